@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""bench.py -- field-elements/s of the SDA hot path (share-gen + clerk-sum) on N B200s.
+
+Workload (BASELINE.json config #3, the configuration the share-gen target is quoted on):
+packed Shamir k=3 / n=5 (t=2) over p = 2^61-1, dim = 10M secrets per participant.  One *step*
+is one pass of the hot path over one resident tile of T participants per GPU:
+    K2  sda_share_generate_dev   secrets[T][dim]      -> shares[T][5][B]      (B = ceil(dim/3))
+    K3  sda_share_combine_dev x5 shares[T][c][B]      -> clerk_sum[c][B]      (one per clerk)
+    N>1 one NCCL reduce (uint64 sum) of clerk_sum[5][B] over the ranks + one mod-p pass on rank 0
+(participants are sharded across GPUs: weak scaling, no other data-path collective).
+`value` = secrets processed by all ranks / max-over-ranks device time, inputs resident in HBM.
+`e2e`   = the same metric through the host-buffer C-ABI calls a Rust shim would make
+          (sda_share_generate per participant, sda_share_combine per clerk), pinned host buffers,
+          H2D and D2H inside the timed region.
+`--impl reference` times the reference's own CPU algorithm (the oracle's literal restatement:
+per-batch Newton interpolation as tss 0.2 does, signed i64 `%`) on all host cores.
+"""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "field-elements/sec (share-gen + clerk-sum)"
+UNIT = "field-elements/s"
+DIM = 10_000_000
+K, T_PRIV, N_SHARES = 3, 2, 5
+
+
+def seeds_for(step, rank, count):
+    return b"".join(hashlib.sha256(b"bench/%d/%d/%d" % (step, rank, i)).digest() for i in range(count))
+
+
+def workload_config(args, world):
+    return {
+        "workload": "config#3 packed Shamir k=3/n=5 t=2, p=2^61-1, dim=10M: share-gen + per-clerk combine"
+                    + (" + NCCL reduce of clerk sums" if world > 1 else ""),
+        "dim": DIM, "participants_per_gpu_per_step": args.participants, "participants_total_config": 4096,
+        "prime_modulus": (1 << 61) - 1, "omega_secrets": "order 7", "omega_shares": "order 11",
+        "rng": f"ChaCha{args.rounds} keystream, rand-0.3 gen_range", "parallelism": f"participants sharded x{world}",
+        "l2": "inputs (>= 10 GB per step) far exceed the 126 MB L2; no flush needed",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle's literal restatement on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_step(O, scheme_o, modulus, dim, participants, threads, tag):
+    """generate + per-clerk combine for `participants` vectors of `dim`, one participant per thread"""
+    import numpy as np
+    n = scheme_o.share_count
+    B = (dim + scheme_o.secret_count - 1) // scheme_o.secret_count
+    secrets = [O.synth_fill(3, modulus, i * dim, dim) for i in range(participants)]
+    shares = [None] * participants
+    t0 = time.perf_counter()
+
+    def work(i):
+        rng = O.rng_from_seed_bytes(hashlib.sha256(b"%s/%d" % (tag.encode(), i)).digest())
+        shares[i] = O.share_generate(scheme_o, secrets[i], rng)
+
+    ths = []
+    for base in range(0, participants, threads):
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(base, min(participants, base + threads))]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+    stacked = np.stack(shares)          # [P][n][B]
+
+    def comb(c):
+        O.share_combine(modulus, np.ascontiguousarray(stacked[:, c, :]))
+
+    ths = [threading.Thread(target=comb, args=(c,)) for c in range(n)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    dt = time.perf_counter() - t0
+    assert stacked.shape == (participants, n, B)
+    return dt
+
+
+def oracle_scheme(O):
+    from sda_b200 import params
+    c = params.config3().c
+    return O.SharingScheme(c.kind, c.share_count, c.secret_count, c.privacy_threshold, c.modulus, c.omega_secrets,
+                           c.omega_shares), c.modulus
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    O.build()
+    so, m = oracle_scheme(O)
+    cores = os.cpu_count() or 1
+    dim_s = args.ref_dim
+    # calibrate so that one step is about ref_seconds
+    t = cpu_step(O, so, m, min(dim_s, 50_000), cores, cores, "cal")
+    per_el = t / (min(dim_s, 50_000) * cores)
+    dim_s = int(max(30_000, min(DIM, args.ref_seconds / (per_el * cores))))
+    for w in range(args.warmup):
+        cpu_step(O, so, m, dim_s, cores, cores, f"w{w}")
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cpu_step(O, so, m, dim_s, cores, cores, f"s{s}")
+    dt = time.perf_counter() - t0
+    value = args.steps * cores * dim_s / dt
+    sample = f"{cores} participants x {dim_s} secrets per step (of dim 10M), one participant per thread"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "i64 (mod 2^61-1, 128-bit products)", "data": "synthetic",
+        "config": dict(workload_config(args, 1), sample=sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference = snipsco/sda's CPU algorithm restated in C (oracle/sda_oracle.c: per-batch Newton "
+                "interpolation like tss 0.2, widened to 128-bit products for the 61-bit prime; injected ChaCha20 "
+                "instead of one getrandom(2) per draw). The Rust crate itself cannot be built in this image.",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(power))
+        return out
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """per-launch DRAM bytes of the share-gen kernel from the committed ncu capture, if any"""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import sda_b200
+    from sda_b200 import params
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sda_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = sda_b200.Context(local, rng_rounds=args.rounds)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    scheme = params.config3()
+    p = scheme.modulus
+    T, dim, n = args.participants, DIM, N_SHARES
+    B = scheme.batches(dim)
+
+    with torch.cuda.stream(stream):
+        d_sec = torch.empty((T, dim), dtype=torch.int64, device="cuda")
+        d_sh = torch.empty((T, n, B), dtype=torch.int64, device="cuda")
+        d_sum = torch.empty((n, B), dtype=torch.int64, device="cuda")
+        d_tot = torch.empty((n, B), dtype=torch.int64, device="cuda")
+        # synthetic canonical secrets, generated on the device (untimed); rank-distinct
+        ctx.synth_fill_dev(3, p, rank * T * dim, T * dim, d_sec)
+        ctx.synchronize()
+
+        ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+        gen_ms, comb_ms = [], []
+
+        def step(i, timed):
+            seeds = seeds_for(i, rank, T)
+            a, b, c = ev(), ev(), ev()
+            a.record(stream)
+            ctx.share_generate_dev(scheme, d_sec, dim, T, dim, seeds, d_sh)
+            b.record(stream)
+            for cl in range(n):
+                ctx.share_combine_dev(scheme, d_sh[:, cl, :], n * B, T, B, d_sum[cl])
+            if world > 1:
+                # canonical partials < p: the uint64 sum of <= 8 of them cannot wrap
+                dist.reduce(d_sum, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    ctx.mod_reduce_dev(p, d_sum, n * B, d_tot, unsigned=True)
+            c.record(stream)
+            if timed:
+                return a, b, c
+            return None
+
+        for w in range(args.warmup):
+            step(-1 - w, False)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        launches0 = ctx.launch_count()
+        t_start, t_end = ev(), ev()
+        torch.cuda.synchronize()
+        t_start.record(stream)
+        marks = [step(i, True) for i in range(args.steps)]
+        t_end.record(stream)
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        clocks = sampler.stop() if sampler else None
+        launches = ctx.launch_count() - launches0
+        total_ms = t_start.elapsed_time(t_end)
+        for a, b, c in marks:
+            gen_ms.append(a.elapsed_time(b))
+            comb_ms.append(b.elapsed_time(c))
+        kernel_name = ctx.last_kernel()
+
+        # correctness spot check of what was just timed (cheap, outside the timed region):
+        # reveal(clerk sums) == column sums of the secrets
+        if rank == 0 and world == 1:
+            d_rec = torch.empty(dim, dtype=torch.int64, device="cuda")
+            d_ref = torch.empty(dim, dtype=torch.int64, device="cuda")
+            ctx.secret_reconstruct_dev(scheme, dim, list(range(n)), d_sum, B, n, B, d_rec)
+            ctx.share_combine_dev(scheme, d_sec, dim, T, dim, d_ref)
+            ctx.synchronize()
+            if not torch.equal(d_rec, d_ref):
+                raise SystemExit("bench self-check failed: reveal(clerk sums) != sum of secrets")
+            del d_rec, d_ref
+
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    value = world * T * dim * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host-buffer C-ABI calls, copies inside the timed region ----------------------------
+    Te = args.e2e_participants
+    h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
+    h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
+    h_rows = ctx.pinned_empty(Te * B).reshape(Te, B)
+    h_out = ctx.pinned_empty(n * B).reshape(n, B)
+    for i in range(Te):
+        h_sec[i][:] = d_sec[i].cpu().numpy()
+
+    def e2e_step(i):
+        seeds = seeds_for(1000 + i, rank, Te)
+        for q in range(Te):
+            ctx.share_generate(scheme, h_sec[q], seeds[32 * q:32 * q + 32], out=h_sh[q])
+        for cl in range(n):
+            # the clerk receives its column of every participation (server snapshot transpose)
+            np.copyto(h_rows, h_sh[:, cl, :])
+            ctx.share_combine(scheme, h_rows, out=h_out[cl])
+
+    e2e_step(-1)
+    if world > 1:
+        dist.barrier()
+    e2e_steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e2e_s = time.perf_counter() - t0
+    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * Te * dim * e2e_steps / float(t_e.item())
+    h2d = Te * dim * 8 + n * Te * B * 8
+    d2h = Te * n * B * 8 + n * B * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (K2 share-gen) --------------------------------------------
+    peak, peak_src = load_peaks()
+    alg_bytes = T * (dim * 8 + n * B * 8)                       # read secrets + write shares
+    gen_avg_ms = sum(gen_ms) / len(gen_ms)
+    achieved = alg_bytes / (gen_avg_ms * 1e-3) / 1e9
+    comb_bytes = n * (T * B * 8 + B * 8)
+    comb_avg_ms = sum(comb_ms) / len(comb_ms)
+    traffic = load_traffic()
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic.get("packed_share_bytes_per_launch"),
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": gen_avg_ms,
+                "share_of_step": gen_avg_ms / (gen_avg_ms + comb_avg_ms)}
+    kernels = {
+        "share_gen": {"ms": gen_avg_ms, "elements_per_s": T * dim / (gen_avg_ms * 1e-3), "GBps": achieved,
+                      "frac_of_hbm": achieved / peak},
+        "clerk_combine_x5": {"ms": comb_avg_ms, "share_elements_per_s": n * T * B / (comb_avg_ms * 1e-3),
+                             "GBps": comb_bytes / (comb_avg_ms * 1e-3) / 1e9,
+                             "frac_of_hbm": comb_bytes / (comb_avg_ms * 1e-3) / 1e9 / peak,
+                             "includes": "NCCL reduce + mod pass" if world > 1 else "5 combine launches"},
+    }
+
+    # ---- cpu baseline beside it (bounded sample, rank 0, N=1 only) ---------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        so, m = oracle_scheme(O)
+        cal = cpu_step(O, so, m, 20_000, 1, 1, "cal")
+        dim_s = int(max(20_000, min(DIM, args.cpu_seconds / (cal / 20_000))))
+        dt = cpu_step(O, so, m, dim_s, 1, 1, "cpu")
+        cpu = {"value": dim_s / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"1 participant x {dim_s} secrets (of dim 10M): literal per-batch share-gen + combine, "
+                         f"single thread like the reference client; host has {os.cpu_count()} cores"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (Z_p, p=2^61-1; 32x32->64 IMAD limbs)", "data": "synthetic",
+        "config": workload_config(args, world), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "participants_per_step": Te, "api": "sda_share_generate + sda_share_combine (pinned host buffers)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--participants", type=int, default=256, help="resident participants per GPU per step")
+    ap.add_argument("--rounds", type=int, default=20, choices=[8, 12, 20], help="ChaCha rounds of the sharing randomness")
+    ap.add_argument("--e2e-participants", type=int, default=4)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-seconds", type=float, default=6.0, help="target CPU seconds per reference step")
+    ap.add_argument("--ref-dim", type=int, default=500_000)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,212 @@
+/*
+ * sda_b200.h -- C ABI of libsda_b200.so: the B200-native replacement for the data-parallel
+ * hot path of snipsco/sda (participant-side masking + secret sharing, clerk-side share
+ * summation, recipient-side reconstruction + unmasking).
+ *
+ * The reference (Rust, CPU) has no FFI seam; the seam is its trait surface.  Each entry point
+ * below is what a Rust shim implementing that trait on `CryptoModule` binds (bindings/rust,
+ * INTEGRATION.md).  Citations are paths relative to the reference tree (snipsco/sda @ 8cf97f2).
+ *
+ *   trait / type                                   reference                                entry point
+ *   ---------------------------------------------  ---------------------------------------  --------------------------
+ *   LinearSecretSharingScheme                      protocol/src/crypto.rs:79-114            sda_sharing_scheme
+ *   LinearMaskingScheme                            protocol/src/crypto.rs:43-64             sda_masking_scheme
+ *   input_size/output_size/..._threshold           protocol/src/crypto.rs:117-155           sda_input_size ...
+ *   ShareGenerator::generate                       client/src/crypto/sharing/mod.rs:14-17   sda_share_generate
+ *     (batched.rs:18-53, additive.rs:32-51, packed_shamir.rs:40-43)
+ *   ShareCombiner::combine                         client/src/crypto/sharing/mod.rs:23-25   sda_share_combine[_rows]
+ *     (combiner.rs:15-29)
+ *   SecretReconstructor::reconstruct               client/src/crypto/sharing/mod.rs:31-33   sda_secret_reconstruct[_rows]
+ *     (additive.rs:55-73, batched.rs:68-97, packed_shamir.rs:73-77)
+ *   SecretMasker::mask                             client/src/crypto/masking/mod.rs:13-15   sda_mask
+ *     (none.rs:13-19, full.rs:21-35, chacha.rs:24-54)
+ *   MaskCombiner::combine                          client/src/crypto/masking/mod.rs:21-23   sda_mask_combine
+ *     (none.rs:21-26, full.rs:37-52, chacha.rs:56-77)
+ *   SecretUnmasker::unmask                         client/src/crypto/masking/mod.rs:29-31   sda_unmask
+ *     (none.rs:28-33, full.rs:54-66, chacha.rs:79-92)
+ *   RecipientOutput::positive                      client/src/receive.rs:13-21              (outputs are already canonical)
+ *
+ * Conventions
+ *   - Element type is int64_t (`Secret/Mask/MaskedSecret/Share = i64`, client/src/crypto/mod.rs:33-36).
+ *   - Inputs may be ANY i64 (negative, >= modulus).  Outputs are always canonical residues in
+ *     [0, modulus) -- i.e. what the reference yields after RecipientOutput::positive(); the
+ *     reference's raw outputs are signed representatives of the same classes.
+ *   - Caller allocates every output; sizes follow from the scheme (helpers below).  Nothing is
+ *     allocated across the boundary, no callbacks, no global mutable state outside sda_ctx.
+ *   - Randomness is injected: `rng_seed` is 32 bytes of caller entropy (the Rust shim fills it
+ *     from OsRng).  The result is exactly the reference algorithm run with its `OsRng` replaced
+ *     by rand-0.3 `ChaChaRng::from_seed(seed as 8 LE u32 words)` (ChaCha with the context's
+ *     round count, default 20) and draws taken by `Rng::gen_range` in the reference's order.
+ *   - Return value: SDA_OK, or an error class; sda_last_error() gives the message, which for
+ *     class SDA_ERR_INVALID is the reference's own Err string / panic message.
+ *   - A context is not thread-safe; use one per thread (they are cheap) or lock externally.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SDA_ERR_CUDA.
+ */
+#ifndef SDA_B200_H
+#define SDA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDA_B200_ABI_VERSION 1
+
+enum {
+    SDA_OK = 0,
+    SDA_ERR_INVALID = 1,     /* the reference returns Err(..) or panics on this input */
+    SDA_ERR_CUDA = 2,        /* CUDA runtime / driver failure (incl. no device) */
+    SDA_ERR_NCCL = 3,        /* reserved: collectives are driven by the host layer */
+    SDA_ERR_UNSUPPORTED = 4  /* parameters outside what the kernels implement */
+};
+
+enum { SDA_SHARING_ADDITIVE = 0, SDA_SHARING_PACKED_SHAMIR = 1 };
+enum { SDA_MASK_NONE = 0, SDA_MASK_FULL = 1, SDA_MASK_CHACHA = 2 };
+
+/* protocol/src/crypto.rs:79-114.  Additive uses share_count + modulus only. */
+typedef struct {
+    int32_t  kind;
+    uint64_t share_count, secret_count, privacy_threshold;
+    int64_t  modulus;        /* `modulus` | `prime_modulus` */
+    int64_t  omega_secrets, omega_shares;
+} sda_sharing_scheme;
+
+/* protocol/src/crypto.rs:43-64 */
+typedef struct {
+    int32_t  kind;
+    int64_t  modulus;
+    uint64_t dimension, seed_bitsize;   /* ChaCha only */
+} sda_masking_scheme;
+
+typedef struct sda_ctx sda_ctx;
+
+/* ---- context -------------------------------------------------------------------------- */
+int         sda_abi_version(void);
+int         sda_ctx_create(int device, sda_ctx **out);
+void        sda_ctx_destroy(sda_ctx *ctx);
+/* message of the last failing call on this context (ctx == NULL: of the last failing
+ * sda_ctx_create on this thread) */
+const char *sda_last_error(const sda_ctx *ctx);
+/* ChaCha rounds of the injected sharing / Full-mask randomness: 8, 12 or 20 (default 20).
+ * The ChaCha *mask scheme* (chacha.rs) is wire format and always uses 20. */
+int         sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds);
+int         sda_ctx_get_rng_rounds(const sda_ctx *ctx);
+/* stream (cudaStream_t) the *_dev entry points launch on; default: a context-owned stream */
+int         sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream);
+void       *sda_ctx_get_stream(const sda_ctx *ctx);
+int         sda_ctx_synchronize(sda_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t    sda_ctx_launch_count(const sda_ctx *ctx);
+/* kernel variant the last sharing call dispatched to ("packed<3,2,5>/mersenne61", ...) */
+const char *sda_ctx_last_kernel(const sda_ctx *ctx);
+/* pinned host memory for callers that want DMA-speed host entry points (optional) */
+int         sda_host_alloc(sda_ctx *ctx, size_t bytes, void **out);
+int         sda_host_free(sda_ctx *ctx, void *ptr);
+
+/* ---- derived scheme properties (protocol/src/crypto.rs:117-155) ------------------------ */
+size_t sda_input_size(const sda_sharing_scheme *s);
+size_t sda_output_size(const sda_sharing_scheme *s);
+size_t sda_privacy_threshold(const sda_sharing_scheme *s);
+size_t sda_reconstruction_threshold(const sda_sharing_scheme *s);
+/* ceil(dim / input_size): length of each clerk's share vector (batched.rs:23) */
+size_t sda_share_batches(const sda_sharing_scheme *s, size_t dim);
+/* length of the mask SecretMasker::mask returns: 0 | dim | ceil(seed_bitsize/32) */
+size_t sda_mask_len(const sda_masking_scheme *s, size_t dim);
+/* 0 if the scheme is usable, else an error class (message via sda_last_error(ctx)) */
+int    sda_sharing_scheme_validate(sda_ctx *ctx, const sda_sharing_scheme *s);
+/* the n x (k+t) share matrix M (row-major, canonical) with shares = M.[secrets;randomness]:
+ * what packed_shamir.rs:42 (tss share) evaluates per batch.  Diagnostic / test hook. */
+int    sda_packed_share_matrix(sda_ctx *ctx, const sda_sharing_scheme *s, int64_t *out);
+/* the k x m reconstruction matrix R for a clerk index subset (packed_shamir.rs:76) */
+int    sda_packed_reconstruct_matrix(sda_ctx *ctx, const sda_sharing_scheme *s,
+                                     const uint64_t *indices, size_t m, int64_t *out);
+
+/* ---- host-pointer entry points (the drop-in trait methods) ----------------------------- */
+
+/* ShareGenerator::generate.  shares_out is [output_size][ceil(dim/input_size)], clerk-major
+ * (row r is the Vec<Share> addressed to clerk r). */
+int sda_share_generate(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *secrets, size_t dim,
+                       const uint8_t rng_seed[32], int64_t *shares_out);
+
+/* ShareCombiner::combine on a contiguous participant-major matrix shares[P][L]. */
+int sda_share_combine(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *shares, size_t P, size_t L,
+                      int64_t *out /* [L] */);
+/* Same on `&Vec<Vec<Share>>` as it lies in Rust memory: P row pointers + lengths.  Rows whose
+ * length differs from row 0's fail with "Wrong dimension" (combiner.rs:21).  *out_len = row 0's
+ * length (0 when P == 0). */
+int sda_share_combine_rows(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *rows,
+                           const size_t *row_lens, size_t P, int64_t *out, size_t *out_len);
+
+/* SecretReconstructor::reconstruct on shares[m][B] (row s = clerk indices[s]'s combined vector).
+ * Additive: column sum, indices ignored, *out_len = B (additive.rs:55-73).
+ * Packed:   *out_len = dimension; needs m >= reconstruction_threshold
+ *           ("Not enough shares to reconstruct") and B >= ceil(dimension/k). */
+int sda_secret_reconstruct(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                           const int64_t *shares, size_t m, size_t B, int64_t *secrets_out, size_t *out_len);
+int sda_secret_reconstruct_rows(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension,
+                                const uint64_t *indices, const int64_t *const *rows, const size_t *row_lens,
+                                size_t m, int64_t *secrets_out, size_t *out_len);
+
+/* SecretMasker::mask -> (mask, masked).  mask_out needs sda_mask_len() elements. */
+int sda_mask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *secrets, size_t dim,
+             const uint8_t rng_seed[32], int64_t *mask_out, size_t *mask_len, int64_t *masked_out);
+/* MaskCombiner::combine on masks[P][mask_len]; out needs dim (Full: mask_len; ChaCha:
+ * scheme.dimension) elements. */
+int sda_mask_combine(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *masks, size_t P, size_t mask_len,
+                     int64_t *out, size_t *out_len);
+/* SecretUnmasker::unmask on (mask, masked). */
+int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, size_t mask_len,
+               const int64_t *masked, size_t dim, int64_t *out);
+
+/* ---- device-pointer entry points (what the benchmark times) ---------------------------- */
+/* All pointers are device memory of the context's device; launches go to the context's
+ * stream.  Calls that draw randomness synchronise that stream once at the end to read the
+ * gen_range rejection flag (and redo the call on the exact path if it is set). */
+
+/* ShareGenerator::generate for P participants at once: secrets[P][dim] (row stride
+ * secrets_ld elements), seeds[P][32] (HOST memory), shares_out[P][output_size][B]. */
+int sda_share_generate_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t secrets_ld,
+                           size_t P, size_t dim, const uint8_t *seeds, int64_t *d_shares_out);
+
+/* ShareCombiner::combine: out[i] = sum_p shares[p*ld + i] mod m.  If d_acc_in != NULL it is
+ * added as one more row (streaming tiles into a running sum: clerk.rs:71-72 FIXME). */
+int sda_share_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld, size_t P,
+                          size_t L, const int64_t *d_acc_in, int64_t *d_out);
+
+/* Fused participant->clerk path for one box: shares of P participants are
+ * generated and summed per clerk without materialising [P][n][B]:
+ * out[n][B] (+= d_acc_in[n][B] if given) = sum_p generate(secrets[p]) . */
+int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets,
+                                   size_t secrets_ld, size_t P, size_t dim, const uint8_t *seeds,
+                                   const int64_t *d_acc_in, int64_t *d_out);
+
+/* x -> x mod m over a vector (final pass after an NCCL sum of canonical partial sums). */
+int sda_mod_reduce_dev(sda_ctx *ctx, int64_t modulus, const int64_t *d_in, size_t n, int64_t *d_out);
+/* same with the input read as u64: the pass after an ncclSum of G canonical partial sums,
+ * exact while G * modulus <= 2^64 (8 GPUs at a 61-bit modulus). */
+int sda_mod_reduce_u64_dev(sda_ctx *ctx, int64_t modulus, const uint64_t *d_in, size_t n, int64_t *d_out);
+
+/* d_shares[m][ld], the first B columns of each row are that clerk's vector */
+int sda_secret_reconstruct_dev(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                               const int64_t *d_shares, size_t ld, size_t m, size_t B, int64_t *d_secrets_out);
+
+int sda_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secrets, size_t dim,
+                 const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out);
+int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_masks, size_t P,
+                         size_t mask_len, int64_t *d_out);
+int sda_unmask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_mask, const int64_t *d_masked,
+                   size_t dim, int64_t *d_out);
+
+/* Synthetic benchmark / test inputs, generated on the device: out[i] = value(start + i) where
+ * value(e) = u64 draw e of ChaCha20(key "sda-b200-synthetic-v1", key word 7 = stream) mod m.
+ * Same definition as the oracle's sdao_synth_fill. */
+int sda_synth_fill_dev(sda_ctx *ctx, uint32_t stream, int64_t modulus, uint64_t start, size_t count,
+                       int64_t *d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDA_B200_H */

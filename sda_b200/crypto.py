@@ -1,0 +1,434 @@
+"""Host-side mirror of `sda_client::crypto` over the C ABI (include/sda_b200.h).
+
+Same names, argument meaning and error behaviour as the reference's trait surface
+(client/src/crypto/sharing/mod.rs:10-33, client/src/crypto/masking/mod.rs:9-31) so that tests
+read like the reference's own (`integration-tests/tests/full_loop.rs`):
+
+    crypto = CryptoModule()
+    shares = crypto.new_share_generator(scheme).generate(secrets)          # Vec<Vec<Share>>
+    summed = crypto.new_share_combiner(scheme).combine(rows)               # Vec<Share>
+    output = crypto.new_secret_reconstructor(scheme, dim).reconstruct(indexed_shares)
+
+Every method is a thin call into libsda_b200.so (hand-written sm_100a kernels).  There is no
+Python/numpy implementation of any of them here; without the library or a GPU they raise.
+Where the reference returns `Err(msg)` or panics, `SdaClientError` carries the same message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import sda_masking_scheme, sda_sharing_scheme
+
+
+class SdaClientError(Exception):
+    """`SdaClientResult::Err` (client/src/errors.rs) or a reference panic; `.code` is the C error class."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+        self.message = message
+
+
+# ---- protocol/src/crypto.rs:79-155 -------------------------------------------------------------
+class LinearSecretSharingScheme:
+    """`sda_protocol::LinearSecretSharingScheme` (protocol/src/crypto.rs:79-114)."""
+
+    def __init__(self, c):
+        self.c = c
+
+    @classmethod
+    def Additive(cls, share_count, modulus):
+        return cls(sda_sharing_scheme(_lib.SHARING_ADDITIVE, share_count, 0, 0, modulus, 0, 0))
+
+    @classmethod
+    def PackedShamir(cls, secret_count, share_count, privacy_threshold, prime_modulus, omega_secrets, omega_shares):
+        return cls(sda_sharing_scheme(_lib.SHARING_PACKED_SHAMIR, share_count, secret_count, privacy_threshold,
+                                      prime_modulus, omega_secrets, omega_shares))
+
+    @property
+    def modulus(self):
+        return self.c.modulus
+
+    def is_additive(self):
+        return self.c.kind == _lib.SHARING_ADDITIVE
+
+    def input_size(self):
+        return _lib.load().sda_input_size(C.byref(self.c))
+
+    def output_size(self):
+        return _lib.load().sda_output_size(C.byref(self.c))
+
+    def privacy_threshold(self):
+        return _lib.load().sda_privacy_threshold(C.byref(self.c))
+
+    def reconstruction_threshold(self):
+        return _lib.load().sda_reconstruction_threshold(C.byref(self.c))
+
+    def batches(self, dim):
+        return _lib.load().sda_share_batches(C.byref(self.c), dim)
+
+    def __repr__(self):
+        c = self.c
+        if self.is_additive():
+            return f"Additive{{share_count: {c.share_count}, modulus: {c.modulus}}}"
+        return (f"PackedShamir{{secret_count: {c.secret_count}, share_count: {c.share_count}, "
+                f"privacy_threshold: {c.privacy_threshold}, prime_modulus: {c.modulus}, "
+                f"omega_secrets: {c.omega_secrets}, omega_shares: {c.omega_shares}}}")
+
+
+class LinearMaskingScheme:
+    """`sda_protocol::LinearMaskingScheme` (protocol/src/crypto.rs:43-64)."""
+
+    def __init__(self, c):
+        self.c = c
+
+    @classmethod
+    def None_(cls):
+        return cls(sda_masking_scheme(_lib.MASK_NONE, 0, 0, 0))
+
+    @classmethod
+    def Full(cls, modulus):
+        return cls(sda_masking_scheme(_lib.MASK_FULL, modulus, 0, 0))
+
+    @classmethod
+    def ChaCha(cls, modulus, dimension, seed_bitsize):
+        return cls(sda_masking_scheme(_lib.MASK_CHACHA, modulus, dimension, seed_bitsize))
+
+    def has_mask(self):   # protocol/src/crypto.rs:66-75
+        return self.c.kind != _lib.MASK_NONE
+
+    def mask_len(self, dim):
+        return _lib.load().sda_mask_len(C.byref(self.c), dim)
+
+
+def _i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _seed(rng_seed):
+    """32 bytes of entropy; the reference draws from OsRng at this point (additive.rs:17, full.rs:16)."""
+    s = os.urandom(32) if rng_seed is None else bytes(rng_seed)
+    if len(s) != 32:
+        raise ValueError("rng_seed must be 32 bytes")
+    return (C.c_uint8 * 32).from_buffer_copy(s)
+
+
+def _dev_ptr(t):
+    """device address of a torch CUDA tensor (or a raw int / None)."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class Context:
+    """Owns one `sda_ctx` (device, stream, scratch).  Not thread-safe; one per thread."""
+
+    def __init__(self, device=0, rng_rounds=20):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.sda_ctx_create(device, C.byref(h))
+        if rc:
+            raise SdaClientError(rc, self._lib.sda_last_error(None).decode())
+        self._h = h
+        self.device = device
+        if rng_rounds != 20:
+            self.set_rng_rounds(rng_rounds)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sda_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc:
+            raise SdaClientError(rc, self._lib.sda_last_error(self._h).decode())
+
+    # -- configuration ---------------------------------------------------------------------------
+    def set_rng_rounds(self, rounds):
+        self.check(self._lib.sda_ctx_set_rng_rounds(self._h, rounds))
+
+    def rng_rounds(self):
+        return self._lib.sda_ctx_get_rng_rounds(self._h)
+
+    def set_stream(self, cuda_stream):
+        """cuda_stream: raw cudaStream_t as int (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+        self.check(self._lib.sda_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def stream(self):
+        return self._lib.sda_ctx_get_stream(self._h)
+
+    def synchronize(self):
+        self.check(self._lib.sda_ctx_synchronize(self._h))
+
+    def launch_count(self):
+        return self._lib.sda_ctx_launch_count(self._h)
+
+    def last_kernel(self):
+        return self._lib.sda_ctx_last_kernel(self._h).decode()
+
+    def pinned_empty(self, n, dtype=np.int64):
+        """numpy array over cudaMallocHost memory (kept alive by the array's base object)."""
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self.check(self._lib.sda_host_alloc(self._h, max(nbytes, 1), C.byref(p)))
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(n)).view(_PinnedArray)
+        arr._owner = _PinnedOwner(self, p)
+        return arr
+
+    # -- scheme helpers --------------------------------------------------------------------------
+    def validate(self, scheme):
+        self.check(self._lib.sda_sharing_scheme_validate(self._h, C.byref(scheme.c)))
+
+    def packed_share_matrix(self, scheme):
+        n, w = scheme.c.share_count, scheme.c.secret_count + scheme.c.privacy_threshold
+        out = np.empty((n, w), dtype=np.int64)
+        self.check(self._lib.sda_packed_share_matrix(self._h, C.byref(scheme.c), _ptr(out)))
+        return out
+
+    def packed_reconstruct_matrix(self, scheme, indices):
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        out = np.empty((scheme.c.secret_count, len(idx)), dtype=np.int64)
+        self.check(self._lib.sda_packed_reconstruct_matrix(self._h, C.byref(scheme.c), _ptr(idx), len(idx), _ptr(out)))
+        return out
+
+    # -- host-pointer entry points ---------------------------------------------------------------
+    def share_generate(self, scheme, secrets, rng_seed=None, out=None):
+        sec = _i64(secrets)
+        n, B = scheme.output_size(), scheme.batches(len(sec))
+        if out is None:
+            out = np.empty((n, B), dtype=np.int64)
+        self.check(self._lib.sda_share_generate(self._h, C.byref(scheme.c), _ptr(sec), len(sec), _seed(rng_seed),
+                                                _ptr(out)))
+        return out
+
+    def share_combine(self, scheme, shares, out=None):
+        """shares: 2-D array [P][L] (contiguous fast path) or a list of 1-D rows (`Vec<Vec<Share>>`)."""
+        if isinstance(shares, np.ndarray) and shares.ndim == 2 and shares.dtype == np.int64:
+            sh = np.ascontiguousarray(shares)
+            P, L = sh.shape
+            if out is None:
+                out = np.empty(L if P else 0, dtype=np.int64)
+            self.check(self._lib.sda_share_combine(self._h, C.byref(scheme.c), _ptr(sh), P, L, _ptr(out)))
+            return out
+        rows = [_i64(r) for r in shares]
+        P = len(rows)
+        ptrs = (C.c_void_p * max(P, 1))(*[r.ctypes.data for r in rows])
+        lens = (C.c_size_t * max(P, 1))(*[len(r) for r in rows])
+        L = len(rows[0]) if P else 0
+        if out is None:
+            out = np.empty(L, dtype=np.int64)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_share_combine_rows(self._h, C.byref(scheme.c), ptrs, lens, P, _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def secret_reconstruct(self, scheme, dimension, indexed_shares):
+        """indexed_shares: list of (clerk index, share vector) -- `&Vec<(usize, Vec<Share>)>`."""
+        idx = np.ascontiguousarray(np.asarray([i for i, _ in indexed_shares], dtype=np.uint64))
+        rows = [_i64(r) for _, r in indexed_shares]
+        m = len(rows)
+        ptrs = (C.c_void_p * max(m, 1))(*[r.ctypes.data for r in rows])
+        lens = (C.c_size_t * max(m, 1))(*[len(r) for r in rows])
+        cap = max(dimension, len(rows[0]) if m else 0, 1)
+        out = np.empty(cap, dtype=np.int64)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_secret_reconstruct_rows(self._h, C.byref(scheme.c), dimension, _ptr(idx), ptrs, lens, m,
+                                                         _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def mask(self, scheme, secrets, rng_seed=None):
+        sec = _i64(secrets)
+        dim = len(sec)
+        mk = np.empty(max(scheme.mask_len(dim), 1), dtype=np.int64)
+        masked = np.empty(dim, dtype=np.int64)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_mask(self._h, C.byref(scheme.c), _ptr(sec), dim, _seed(rng_seed), _ptr(mk), C.byref(n),
+                                      _ptr(masked)))
+        return mk[:n.value], masked
+
+    def mask_combine(self, scheme, masks):
+        rows = [_i64(r) for r in masks]
+        P = len(rows)
+        ml = len(rows[0]) if P else 0
+        for r in rows:
+            if len(r) != ml:   # full.rs:43 assert_eq!
+                raise SdaClientError(_lib.SDA_ERR_INVALID, "assertion failed: `(left == right)` (full.rs:43)")
+        mat = np.ascontiguousarray(np.stack(rows)) if P else np.empty((0, 0), dtype=np.int64)
+        cap = max(ml, int(scheme.c.dimension), 1)
+        out = np.empty(cap, dtype=np.int64)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_mask_combine(self._h, C.byref(scheme.c), _ptr(mat), P, ml, _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def unmask(self, scheme, mask, masked):
+        mk, md = _i64(mask), _i64(masked)
+        out = np.empty(len(md), dtype=np.int64)
+        self.check(self._lib.sda_unmask(self._h, C.byref(scheme.c), _ptr(mk), len(mk), _ptr(md), len(md), _ptr(out)))
+        return out
+
+    # -- device-pointer entry points (torch CUDA tensors or raw addresses) ------------------------
+    def share_generate_dev(self, scheme, d_secrets, secrets_ld, P, dim, seeds, d_shares_out):
+        seeds = bytes(seeds)
+        if len(seeds) != 32 * P:
+            raise ValueError("seeds must be P x 32 bytes")
+        buf = (C.c_uint8 * max(len(seeds), 1)).from_buffer_copy(seeds or b"\0")
+        self.check(self._lib.sda_share_generate_dev(self._h, C.byref(scheme.c), _dev_ptr(d_secrets), secrets_ld, P, dim,
+                                                    buf, _dev_ptr(d_shares_out)))
+
+    def share_combine_dev(self, scheme, d_shares, ld, P, L, d_out, d_acc_in=None):
+        self.check(self._lib.sda_share_combine_dev(self._h, C.byref(scheme.c), _dev_ptr(d_shares), ld, P, L,
+                                                   _dev_ptr(d_acc_in), _dev_ptr(d_out)))
+
+    def share_generate_combine_dev(self, scheme, d_secrets, secrets_ld, P, dim, seeds, d_out, d_acc_in=None):
+        seeds = bytes(seeds)
+        buf = (C.c_uint8 * max(len(seeds), 1)).from_buffer_copy(seeds or b"\0")
+        self.check(self._lib.sda_share_generate_combine_dev(self._h, C.byref(scheme.c), _dev_ptr(d_secrets), secrets_ld,
+                                                            P, dim, buf, _dev_ptr(d_acc_in), _dev_ptr(d_out)))
+
+    def mod_reduce_dev(self, modulus, d_in, n, d_out, unsigned=False):
+        f = self._lib.sda_mod_reduce_u64_dev if unsigned else self._lib.sda_mod_reduce_dev
+        self.check(f(self._h, modulus, _dev_ptr(d_in), n, _dev_ptr(d_out)))
+
+    def secret_reconstruct_dev(self, scheme, dimension, indices, d_shares, ld, m, B, d_out):
+        idx = np.ascontiguousarray(np.asarray(indices, dtype=np.uint64))
+        self.check(self._lib.sda_secret_reconstruct_dev(self._h, C.byref(scheme.c), dimension, _ptr(idx),
+                                                        _dev_ptr(d_shares), ld, m, B, _dev_ptr(d_out)))
+
+    def mask_dev(self, scheme, d_secrets, dim, rng_seed, d_mask_out, d_masked_out):
+        self.check(self._lib.sda_mask_dev(self._h, C.byref(scheme.c), _dev_ptr(d_secrets), dim, _seed(rng_seed),
+                                          _dev_ptr(d_mask_out), _dev_ptr(d_masked_out)))
+
+    def mask_combine_dev(self, scheme, d_masks, P, mask_len, d_out):
+        self.check(self._lib.sda_mask_combine_dev(self._h, C.byref(scheme.c), _dev_ptr(d_masks), P, mask_len,
+                                                  _dev_ptr(d_out)))
+
+    def unmask_dev(self, scheme, d_mask, d_masked, dim, d_out):
+        self.check(self._lib.sda_unmask_dev(self._h, C.byref(scheme.c), _dev_ptr(d_mask), _dev_ptr(d_masked), dim,
+                                            _dev_ptr(d_out)))
+
+    def synth_fill_dev(self, stream_id, modulus, start, count, d_out):
+        self.check(self._lib.sda_synth_fill_dev(self._h, stream_id, modulus, start, count, _dev_ptr(d_out)))
+
+
+class _PinnedOwner:
+    def __init__(self, ctx, ptr):
+        self.lib, self.h, self.ptr = ctx._lib, ctx._h, ptr
+        self.ctx = ctx   # keep the context alive
+
+    def __del__(self):
+        try:
+            if self.ptr and self.ctx._h:
+                self.lib.sda_host_free(self.ctx._h, self.ptr)
+        except Exception:
+            pass
+
+
+class _PinnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None:
+            self._owner = getattr(obj, "_owner", None)
+
+
+# ---- the trait objects (client/src/crypto/{sharing,masking}/mod.rs) ------------------------------
+class ShareGenerator:
+    """`ShareGenerator::generate(&mut self, secrets: &[Secret]) -> SdaClientResult<Vec<Vec<Share>>>`"""
+
+    def __init__(self, ctx, scheme):
+        self.ctx, self.scheme = ctx, scheme
+
+    def generate(self, secrets, rng_seed=None):
+        return self.ctx.share_generate(self.scheme, secrets, rng_seed)
+
+
+class ShareCombiner:
+    """`ShareCombiner::combine(&self, shares: &Vec<Vec<Share>>) -> SdaClientResult<Vec<Share>>`"""
+
+    def __init__(self, ctx, scheme):
+        self.ctx, self.scheme = ctx, scheme
+
+    def combine(self, shares):
+        return self.ctx.share_combine(self.scheme, shares)
+
+
+class SecretReconstructor:
+    """`SecretReconstructor::reconstruct(&self, &Vec<(usize, Vec<Share>)>) -> SdaClientResult<Vec<Secret>>`"""
+
+    def __init__(self, ctx, scheme, dimension):
+        self.ctx, self.scheme, self.dimension = ctx, scheme, dimension
+
+    def reconstruct(self, indexed_shares):
+        return self.ctx.secret_reconstruct(self.scheme, self.dimension, indexed_shares)
+
+
+class SecretMasker:
+    """`SecretMasker::mask(&mut self, secrets: &[Secret]) -> (Vec<Mask>, Vec<MaskedSecret>)`"""
+
+    def __init__(self, ctx, scheme):
+        self.ctx, self.scheme = ctx, scheme
+
+    def mask(self, secrets, rng_seed=None):
+        return self.ctx.mask(self.scheme, secrets, rng_seed)
+
+
+class MaskCombiner:
+    """`MaskCombiner::combine(&self, masks: &Vec<Vec<Mask>>) -> Vec<Mask>`"""
+
+    def __init__(self, ctx, scheme):
+        self.ctx, self.scheme = ctx, scheme
+
+    def combine(self, masks):
+        return self.ctx.mask_combine(self.scheme, masks)
+
+
+class SecretUnmasker:
+    """`SecretUnmasker::unmask(&self, values: &(Vec<Mask>, Vec<MaskedSecret>)) -> Vec<Secret>`"""
+
+    def __init__(self, ctx, scheme):
+        self.ctx, self.scheme = ctx, scheme
+
+    def unmask(self, values):
+        mask, masked = values
+        return self.ctx.unmask(self.scheme, mask, masked)
+
+
+class CryptoModule:
+    """`sda_client::crypto::CryptoModule` restricted to the sharing / masking constructions
+    (client/src/crypto/mod.rs:58-66; sharing/mod.rs:35-96; masking/mod.rs:33-94)."""
+
+    def __init__(self, device=0, rng_rounds=20):
+        self.ctx = Context(device, rng_rounds)
+
+    def new_share_generator(self, scheme):
+        self.ctx.validate(scheme)
+        return ShareGenerator(self.ctx, scheme)
+
+    def new_share_combiner(self, scheme):
+        return ShareCombiner(self.ctx, scheme)
+
+    def new_secret_reconstructor(self, scheme, dimension):
+        return SecretReconstructor(self.ctx, scheme, dimension)
+
+    def new_secret_masker(self, scheme):
+        return SecretMasker(self.ctx, scheme)
+
+    def new_mask_combiner(self, scheme):
+        return MaskCombiner(self.ctx, scheme)
+
+    def new_secret_unmasker(self, scheme):
+        return SecretUnmasker(self.ctx, scheme)

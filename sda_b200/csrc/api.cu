@@ -1,0 +1,1067 @@
+// api.cu -- the C ABI of include/sda_b200.h: context, scheme validation with the reference's
+// error strings, host-side precomputation (reduction constants, share matrix M, reconstruction
+// matrix R), staging of host buffers, and dispatch to the sm_100a kernels.  There is no CPU
+// implementation of any hot-path function in this file: every entry point ends in kernel
+// launches and fails with SDA_ERR_CUDA when there is no device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sda_b200.h"
+#include "kernels.h"
+
+using namespace sda;
+
+namespace {
+
+typedef unsigned __int128 u128;
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct sda_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rounds = 20;
+    uint64_t nlaunch = 0;
+    const char *kernel_name = "";
+    std::string err;
+    DevBuf in, out, aux, scratch, draws, keys, mat;
+    unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
+    unsigned *h_flag = nullptr;    // pinned mirror
+    PinBuf stage[2];               // pinned staging for pageable host buffers
+    LaunchCtx lc() { return LaunchCtx{stream, &nlaunch, sm_count, &kernel_name}; }
+};
+
+namespace {
+
+int fail(sda_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(ctx, SDA_ERR_CUDA, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define OK(call)               \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_) return rc_;   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- host field arithmetic (parameter precomputation only) ------------------------------------
+uint64_t mulmod_h(uint64_t a, uint64_t b, uint64_t p) { return (uint64_t)((u128)a * b % p); }
+uint64_t submod_h(uint64_t a, uint64_t b, uint64_t p) { return a >= b ? a - b : a + p - b; }
+uint64_t powmod_h(uint64_t x, uint64_t e, uint64_t p) {
+    uint64_t r = 1 % p;
+    x %= p;
+    while (e) {
+        if (e & 1) r = mulmod_h(r, x, p);
+        x = mulmod_h(x, x, p);
+        e >>= 1;
+    }
+    return r;
+}
+// inverse by extended Euclid; returns false when gcd(a, p) != 1
+bool invmod_h(uint64_t a, uint64_t p, uint64_t *out) {
+    __int128 r0 = p, r1 = a % p, t0 = 0, t1 = 1;
+    while (r1 != 0) {
+        __int128 q = r0 / r1, tmp = r0 - q * r1;
+        r0 = r1;
+        r1 = tmp;
+        tmp = t0 - q * t1;
+        t0 = t1;
+        t1 = tmp;
+    }
+    if (r0 != 1) return false;
+    if (t0 < 0) t0 += p;
+    *out = (uint64_t)t0;
+    return true;
+}
+uint64_t canon_h(int64_t v, uint64_t p) {
+    int64_t r = (int64_t)(v % (int64_t)p);
+    return (uint64_t)(r < 0 ? r + (int64_t)p : r);
+}
+
+// Lagrange basis value  l_i(x) = prod_{l != i} (x - z_l) / (z_i - z_l)  over nodes z
+bool lagrange_h(const std::vector<uint64_t> &z, size_t i, uint64_t x, uint64_t p, uint64_t *out) {
+    uint64_t num = 1, den = 1;
+    for (size_t l = 0; l < z.size(); l++) {
+        if (l == i) continue;
+        num = mulmod_h(num, submod_h(x, z[l], p), p);
+        den = mulmod_h(den, submod_h(z[i], z[l], p), p);
+    }
+    uint64_t inv;
+    if (!invmod_h(den, p, &inv)) return false;
+    *out = mulmod_h(num, inv, p);
+    return true;
+}
+
+struct Packed {
+    int k, t, n;
+    uint64_t p;
+    std::vector<uint64_t> a;   // secret-side points w_secrets^i, i = 0..k+t
+    std::vector<uint64_t> b;   // share-side points  w_shares^j,  j = 1..n
+};
+
+const char *kind_name(int kind) { return kind == SDA_SHARING_ADDITIVE ? "Additive" : "PackedShamir"; }
+
+int validate(sda_ctx *ctx, const sda_sharing_scheme *s, Packed *pk) {
+    if (!s) return fail(ctx, SDA_ERR_INVALID, "null scheme");
+    if (s->kind == SDA_SHARING_ADDITIVE) {
+        if (s->share_count == 0)   // additive.rs:42 `share_count - 1` underflows
+            return fail(ctx, SDA_ERR_INVALID, "attempt to subtract with overflow (additive.rs:42: share_count = 0)");
+        if (s->modulus <= 0)       // rand 0.3 gen_range: assert!(low < high)
+            return fail(ctx, SDA_ERR_INVALID, "Rng.gen_range called with low >= high");
+        if (s->share_count > 65535)
+            return fail(ctx, SDA_ERR_UNSUPPORTED, "share_count %llu > 65535", (unsigned long long)s->share_count);
+        return SDA_OK;
+    }
+    if (s->kind != SDA_SHARING_PACKED_SHAMIR) return fail(ctx, SDA_ERR_INVALID, "unknown sharing scheme kind %d", s->kind);
+    const uint64_t k = s->secret_count, t = s->privacy_threshold, n = s->share_count;
+    if (k == 0 || n == 0) return fail(ctx, SDA_ERR_INVALID, "PackedShamir needs secret_count >= 1 and share_count >= 1");
+    if (k > (uint64_t)MAX_K || k + t > (uint64_t)MAX_W || n > (uint64_t)MAX_N)
+        return fail(ctx, SDA_ERR_UNSUPPORTED, "PackedShamir shape k=%llu t=%llu n=%llu outside k<=%d, k+t<=%d, n<=%d",
+                    (unsigned long long)k, (unsigned long long)t, (unsigned long long)n, MAX_K, MAX_W, MAX_N);
+    if (s->modulus < 3 || (s->modulus & 1) == 0)
+        return fail(ctx, SDA_ERR_INVALID, "PackedShamir prime_modulus must be an odd prime");
+    const uint64_t p = (uint64_t)s->modulus;
+    if (pk) {
+        pk->k = (int)k; pk->t = (int)t; pk->n = (int)n; pk->p = p;
+        const uint64_t ws = canon_h(s->omega_secrets, p), wh = canon_h(s->omega_shares, p);
+        pk->a.resize(k + t + 1);
+        pk->b.resize(n);
+        for (uint64_t i = 0; i <= k + t; i++) pk->a[i] = powmod_h(ws, i, p);
+        for (uint64_t j = 1; j <= n; j++) pk->b[j - 1] = powmod_h(wh, j, p);
+        for (size_t i = 0; i < pk->a.size(); i++)
+            for (size_t l = 0; l < i; l++)
+                if (pk->a[i] == pk->a[l])
+                    return fail(ctx, SDA_ERR_INVALID, "omega_secrets has order <= secret_count + privacy_threshold: "
+                                                      "interpolation points collide");
+        for (size_t i = 0; i < pk->b.size(); i++) {
+            if (pk->b[i] == 1) return fail(ctx, SDA_ERR_INVALID, "omega_shares has order <= share_count: share point equals 1");
+            for (size_t l = 0; l < i; l++)
+                if (pk->b[i] == pk->b[l])
+                    return fail(ctx, SDA_ERR_INVALID, "omega_shares has order <= share_count: share points collide");
+        }
+    }
+    return SDA_OK;
+}
+
+// M[j][i] = l_{i+1}(b_j) over nodes a_0..a_{k+t}; column of a_0 dropped (value fixed to 0)
+int share_matrix(sda_ctx *ctx, const Packed &pk, Matrix *M) {
+    const int w = pk.k + pk.t;
+    M->rows = pk.n;
+    M->cols = w;
+    for (int j = 0; j < pk.n; j++)
+        for (int i = 0; i < w; i++)
+            if (!lagrange_h(pk.a, (size_t)i + 1, pk.b[j], pk.p, &M->e[j * w + i]))
+                return fail(ctx, SDA_ERR_INVALID, "prime_modulus is not prime (non-invertible difference of points)");
+    return SDA_OK;
+}
+
+// R[e][s] = lambda_{s+1}(a_{e+1}) over nodes {1} u {b_{idx_s}}; node-1 column dropped
+int reconstruct_matrix(sda_ctx *ctx, const Packed &pk, const uint64_t *indices, size_t m, Matrix *R) {
+    if (m > (size_t)MAX_N) return fail(ctx, SDA_ERR_UNSUPPORTED, "more than %d indexed shares", MAX_N);
+    std::vector<uint64_t> z(m + 1);
+    z[0] = 1;
+    for (size_t s = 0; s < m; s++) {
+        if (indices[s] >= (uint64_t)pk.n)
+            return fail(ctx, SDA_ERR_INVALID, "share index %llu out of range for share_count %d",
+                        (unsigned long long)indices[s], pk.n);
+        z[s + 1] = pk.b[indices[s]];
+        for (size_t l = 0; l < s; l++)
+            if (indices[l] == indices[s]) return fail(ctx, SDA_ERR_INVALID, "duplicate share index %llu", (unsigned long long)indices[s]);
+    }
+    R->rows = pk.k;
+    R->cols = (int)m;
+    for (int e = 0; e < pk.k; e++)
+        for (size_t s = 0; s < m; s++)
+            if (!lagrange_h(z, s + 1, pk.a[e + 1], pk.p, &R->e[e * m + s]))
+                return fail(ctx, SDA_ERR_INVALID, "prime_modulus is not prime (non-invertible difference of points)");
+    return SDA_OK;
+}
+
+// rand 0.3 ChaChaRng on the host: only for the handful of seed words of the ChaCha mask scheme
+// (chacha.rs:30-33 draws them from OsRng; here they come from the injected rng_seed stream)
+void host_chacha_block(const ChaChaKey &key, uint64_t block, int rounds, uint32_t out[16]) {
+    uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    for (int i = 0; i < 8; i++) st[4 + i] = key.w[i];
+    st[12] = (uint32_t)block;
+    st[13] = (uint32_t)(block >> 32);
+    st[14] = st[15] = 0;
+    uint32_t x[16];
+    memcpy(x, st, sizeof x);
+    auto rotl = [](uint32_t v, int c) { return (v << c) | (v >> (32 - c)); };
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 16);
+        x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 12);
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 8);
+        x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 7);
+    };
+    for (int i = 0; i < rounds / 2; i++) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
+}
+
+// ---- flag handling --------------------------------------------------------------------------
+int clear_flags(sda_ctx *ctx) {
+    CU(cudaMemsetAsync(ctx->d_flag, 0, 2 * sizeof(unsigned), ctx->stream));
+    return SDA_OK;
+}
+int read_flags(sda_ctx *ctx, unsigned *rejected, unsigned *status) {
+    CU(cudaMemcpyAsync(ctx->h_flag, ctx->d_flag, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (rejected) *rejected = ctx->h_flag[0];
+    if (status) *status = ctx->h_flag[1];
+    return SDA_OK;
+}
+
+// exact gen_range stream of `count` samples for one key into ctx->draws (at element offset off)
+int draw_exact(sda_ctx *ctx, const DrawParams &dr, int rounds, const ChaChaKey &key, size_t count, uint64_t *d_out) {
+    if (count == 0) return SDA_OK;
+    const double accept = (double)dr.zone / 18446744073709551616.0;
+    size_t window = (size_t)((double)count / accept * 1.02) + 4096;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        const size_t se = draw_exact_scratch_elems(window);
+        CU(ctx->scratch.reserve(se * sizeof(uint64_t)));
+        OK(clear_flags(ctx));
+        CU(launch_draw_exact(ctx->lc(), dr, rounds, key, count, window, d_out, (uint64_t *)ctx->scratch.p,
+                             ctx->d_flag + 1));
+        unsigned status = 0;
+        OK(read_flags(ctx, nullptr, &status));
+        if (!status) return SDA_OK;
+        window *= 2;
+    }
+    return fail(ctx, SDA_ERR_CUDA, "exact gen_range stream did not converge");
+}
+
+int upload_keys(sda_ctx *ctx, const uint8_t *seeds, size_t P) {
+    std::vector<ChaChaKey> k(P);
+    for (size_t p = 0; p < P; p++) k[p] = key_from_seed_bytes(seeds + 32 * p);
+    CU(ctx->keys.reserve(P * sizeof(ChaChaKey)));
+    CU(cudaMemcpyAsync(ctx->keys.p, k.data(), P * sizeof(ChaChaKey), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // k goes out of scope
+    return SDA_OK;
+}
+
+// ---- host <-> device staging ----------------------------------------------------------------
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+constexpr size_t STAGE_BYTES = 32u << 20;
+
+// pageable -> device through two pinned staging buffers (overlaps the CPU copy with the DMA);
+// pinned -> device directly.  Asynchronous on ctx->stream for the pinned case.
+int h2d(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return SDA_OK;
+    if (is_pinned(src)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SDA_OK;
+    }
+    if (bytes <= (1u << 20)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SDA_OK;
+    }
+    for (int i = 0; i < 2; i++) CU(ctx->stage[i].reserve(STAGE_BYTES));
+    size_t off = 0;
+    int i = 0;
+    while (off < bytes) {
+        const size_t n = std::min(STAGE_BYTES, bytes - off);
+        CU(cudaEventSynchronize(ctx->ev[i]));
+        memcpy(ctx->stage[i].p, (const char *)src + off, n);
+        CU(cudaMemcpyAsync((char *)dst + off, ctx->stage[i].p, n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[i], ctx->stream));
+        off += n;
+        i ^= 1;
+    }
+    return SDA_OK;
+}
+
+// device -> host; returns after the data has landed
+int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return SDA_OK;
+    if (is_pinned(dst) || bytes <= (1u << 20)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return SDA_OK;
+    }
+    for (int i = 0; i < 2; i++) CU(ctx->stage[i].reserve(STAGE_BYTES));
+    size_t off = 0, pend_off[2] = {0, 0}, pend_n[2] = {0, 0};
+    int i = 0;
+    CU(cudaEventSynchronize(ctx->ev[0]));
+    CU(cudaEventSynchronize(ctx->ev[1]));
+    while (off < bytes || pend_n[0] || pend_n[1]) {
+        if (pend_n[i]) {
+            CU(cudaEventSynchronize(ctx->ev[i]));
+            memcpy((char *)dst + pend_off[i], ctx->stage[i].p, pend_n[i]);
+            pend_n[i] = 0;
+        }
+        if (off < bytes) {
+            const size_t n = std::min(STAGE_BYTES, bytes - off);
+            CU(cudaMemcpyAsync(ctx->stage[i].p, (const char *)src + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaEventRecord(ctx->ev[i], ctx->stream));
+            pend_off[i] = off;
+            pend_n[i] = n;
+            off += n;
+        }
+        i ^= 1;
+    }
+    return SDA_OK;
+}
+
+// ---- core device-side operations (shared by host and device entry points) --------------------
+
+int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t ld, size_t P,
+                        size_t dim, const uint8_t *seeds, int64_t *d_out) {
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (P == 0 || dim == 0) return SDA_OK;
+    if (!seeds) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
+    const bool additive = s->kind == SDA_SHARING_ADDITIVE;
+    const FieldParams f = make_field((uint64_t)s->modulus);
+    const int n = (int)s->share_count;
+    Matrix M;
+    DrawParams dr;
+    size_t B, dpe;   // outputs per clerk, draws per output column
+    if (additive) {
+        dr = make_draw((uint64_t)s->modulus);
+        B = dim;
+        dpe = (size_t)n - 1;
+    } else {
+        if (s->modulus < 3) return fail(ctx, SDA_ERR_INVALID, "prime_modulus too small");
+        dr = make_draw((uint64_t)s->modulus - 1);   // tss share(): Range::new(0, prime - 1)
+        OK(share_matrix(ctx, pk, &M));
+        B = (dim + pk.k - 1) / pk.k;
+        dpe = (size_t)pk.t;
+    }
+    OK(upload_keys(ctx, seeds, P));
+    const ChaChaKey *d_keys = (const ChaChaKey *)ctx->keys.p;
+    const bool fast = additive ? (n == 1 || additive_split_has_fast_path(n)) : packed_share_has_fast_path(pk.k, pk.t, pk.n);
+    bool exact = !fast;
+    if (fast) {
+        OK(clear_flags(ctx));
+        for (size_t p0 = 0; p0 < P; p0 += 65535) {
+            const size_t pc = std::min<size_t>(65535, P - p0);
+            if (additive)
+                CU(launch_additive_split(ctx->lc(), f, dr, ctx->rounds, n, d_secrets + p0 * ld, ld, pc, dim, d_keys + p0,
+                                         nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag));
+            else
+                CU(launch_packed_share(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, M, d_secrets + p0 * ld, ld, pc,
+                                       dim, d_keys + p0, nullptr, nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag));
+        }
+        unsigned rejected = 0;
+        OK(read_flags(ctx, &rejected, nullptr));
+        exact = rejected != 0;
+    }
+    if (!exact) return SDA_OK;
+    // exact path: per participant, materialise the gen_range stream, then share from memory
+    const size_t count = B * dpe;
+    CU(ctx->draws.reserve(std::max<size_t>(count, 1) * sizeof(uint64_t)));
+    if (!additive) {
+        CU(ctx->mat.reserve(sizeof(M.e)));
+        CU(cudaMemcpyAsync(ctx->mat.p, M.e, sizeof(M.e), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    for (size_t p = 0; p < P; p++) {
+        const ChaChaKey key = key_from_seed_bytes(seeds + 32 * p);
+        OK(draw_exact(ctx, dr, ctx->rounds, key, count, (uint64_t *)ctx->draws.p));
+        if (additive)
+            CU(launch_additive_split(ctx->lc(), f, dr, ctx->rounds, n, d_secrets + p * ld, ld, 1, dim, d_keys + p,
+                                     (const uint64_t *)ctx->draws.p, d_out + p * (size_t)n * B, ctx->d_flag));
+        else
+            CU(launch_packed_share(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, M, d_secrets + p * ld, ld, 1, dim,
+                                   d_keys + p, (const uint64_t *)ctx->draws.p, (const uint64_t *)ctx->mat.p,
+                                   d_out + p * (size_t)n * B, ctx->d_flag));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDA_OK;
+}
+
+int combine_core(sda_ctx *ctx, int64_t modulus, const int64_t *d_rows, size_t ld, size_t P, size_t L,
+                 const int64_t *d_acc, int64_t *d_out) {
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "attempt to calculate the remainder with a divisor of zero or negative modulus");
+    if (L == 0) return SDA_OK;
+    const FieldParams f = make_field((uint64_t)modulus);
+    const size_t se = combine_scratch_elems(ctx->sm_count, P, L);
+    if (se) CU(ctx->scratch.reserve(se * sizeof(int64_t)));
+    CU(launch_combine(ctx->lc(), f, d_rows, ld, P, L, d_acc, d_out, (int64_t *)ctx->scratch.p, se));
+    return SDA_OK;
+}
+
+int reconstruct_core(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                     const int64_t *d_shares, size_t ld, size_t m, size_t B, int64_t *d_out, size_t *out_len) {
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (s->kind == SDA_SHARING_ADDITIVE) {
+        // additive.rs:55-73: dimension = length of the first share vector; indices ignored
+        const size_t len = m ? B : 0;
+        if (out_len) *out_len = len;
+        return combine_core(ctx, s->modulus, d_shares, ld, m, len, nullptr, d_out);
+    }
+    if (out_len) *out_len = dimension;
+    const size_t nb = (dimension + pk.k - 1) / pk.k;
+    if (nb == 0) return SDA_OK;
+    if (m < (size_t)(pk.t + pk.k)) return fail(ctx, SDA_ERR_INVALID, "Not enough shares to reconstruct");   // packed_shamir.rs:75
+    if (B < nb)   // batched.rs:84 indexes out of bounds -> panic
+        return fail(ctx, SDA_ERR_INVALID, "index out of bounds: the len is %zu but the index is %zu", B, B);
+    if (!indices) return fail(ctx, SDA_ERR_INVALID, "null indices");
+    Matrix R;
+    OK(reconstruct_matrix(ctx, pk, indices, m, &R));
+    const FieldParams f = make_field(pk.p);
+    CU(launch_packed_reconstruct(ctx->lc(), f, pk.k, (int)m, R, d_shares, ld, dimension, d_out));
+    return SDA_OK;
+}
+
+int mask_validate(sda_ctx *ctx, const sda_masking_scheme *s) {
+    if (!s) return fail(ctx, SDA_ERR_INVALID, "null scheme");
+    if (s->kind == SDA_MASK_NONE) return SDA_OK;
+    if (s->kind != SDA_MASK_FULL && s->kind != SDA_MASK_CHACHA)
+        return fail(ctx, SDA_ERR_INVALID, "unknown masking scheme kind %d", s->kind);
+    if (s->modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "Rng.gen_range called with low >= high");
+    if (s->kind == SDA_MASK_CHACHA && (s->seed_bitsize + 31) / 32 > 8)
+        return fail(ctx, SDA_ERR_UNSUPPORTED, "ChaCha seed_bitsize %llu > 256", (unsigned long long)s->seed_bitsize);
+    return SDA_OK;
+}
+
+// Full: mask = dim draws of rng(seed); ChaCha: seed words = first words of rng(seed), mask stream
+// = ChaCha20(seed words).  d_mask_out: Full -> [dim]; ChaCha -> unused (seed words returned in
+// seed_words_out by the caller).
+int mask_core(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secrets, size_t dim,
+              const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *seed_words_out, int64_t *d_masked_out) {
+    OK(mask_validate(ctx, s));
+    if (s->kind == SDA_MASK_NONE) {   // none.rs:14-18
+        if (dim && d_masked_out != d_secrets)
+            CU(cudaMemcpyAsync(d_masked_out, d_secrets, dim * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        return SDA_OK;
+    }
+    if (!rng_seed) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
+    const FieldParams f = make_field((uint64_t)s->modulus);
+    const DrawParams dr = make_draw((uint64_t)s->modulus);
+    ChaChaKey key = key_from_seed_bytes(rng_seed);
+    int rounds = ctx->rounds;
+    int64_t *mask_dst = d_mask_out;
+    if (s->kind == SDA_MASK_CHACHA) {
+        if (s->dimension != dim)   // chacha.rs:26
+            return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (chacha.rs:26: scheme dimension %llu, %zu secrets)",
+                        (unsigned long long)s->dimension, dim);
+        const size_t words = (size_t)((s->seed_bitsize + 31) / 32);   // chacha.rs:30
+        uint32_t blk[16];
+        host_chacha_block(key, 0, ctx->rounds, blk);                  // chacha.rs:31-33, OsRng -> injected stream
+        uint32_t seed[8] = {0};
+        for (size_t i = 0; i < words; i++) {
+            seed[i] = blk[i];
+            if (seed_words_out) seed_words_out[i] = (int64_t)seed[i]; // chacha.rs:48-50
+        }
+        key = key_from_words(seed, words);                            // chacha.rs:36
+        rounds = 20;
+        mask_dst = nullptr;
+    }
+    if (dim == 0) return SDA_OK;
+    OK(clear_flags(ctx));
+    CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, nullptr, mask_dst, d_masked_out, ctx->d_flag));
+    unsigned rejected = 0;
+    OK(read_flags(ctx, &rejected, nullptr));
+    if (!rejected) return SDA_OK;
+    CU(ctx->draws.reserve(dim * sizeof(uint64_t)));
+    OK(draw_exact(ctx, dr, rounds, key, dim, (uint64_t *)ctx->draws.p));
+    CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, (const uint64_t *)ctx->draws.p, mask_dst,
+                   d_masked_out, ctx->d_flag));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDA_OK;
+}
+
+// ChaCha mask combine from host seed rows (P x mask_len i64)
+int chacha_mask_combine_core(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *h_masks, size_t P,
+                             size_t mask_len, int64_t *d_out) {
+    const size_t dim = (size_t)s->dimension;
+    if (dim == 0) return SDA_OK;
+    const FieldParams f = make_field((uint64_t)s->modulus);
+    const DrawParams dr = make_draw((uint64_t)s->modulus);
+    std::vector<ChaChaKey> keys(P);
+    for (size_t p = 0; p < P; p++) {
+        uint32_t w[8] = {0};
+        for (size_t i = 0; i < mask_len && i < 8; i++) w[i] = (uint32_t)h_masks[p * mask_len + i];   // chacha.rs:62-64
+        keys[p] = key_from_words(w, 8);
+    }
+    CU(ctx->keys.reserve(std::max<size_t>(P, 1) * sizeof(ChaChaKey)));
+    if (P) CU(cudaMemcpyAsync(ctx->keys.p, keys.data(), P * sizeof(ChaChaKey), cudaMemcpyHostToDevice, ctx->stream));
+    const size_t se = chacha_mask_combine_scratch_elems(ctx->sm_count, P, dim);
+    if (se) CU(ctx->scratch.reserve(se * sizeof(int64_t)));
+    OK(clear_flags(ctx));
+    CU(launch_chacha_mask_combine(ctx->lc(), f, dr, (const ChaChaKey *)ctx->keys.p, P, dim, d_out,
+                                  (int64_t *)ctx->scratch.p, se, ctx->d_flag));
+    unsigned rejected = 0;
+    OK(read_flags(ctx, &rejected, nullptr));
+    if (!rejected) return SDA_OK;
+    // exact: out = sum over seeds of the exact stream
+    CU(ctx->draws.reserve(dim * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(d_out, 0, dim * sizeof(int64_t), ctx->stream));
+    for (size_t p = 0; p < P; p++) {
+        OK(draw_exact(ctx, dr, 20, keys[p], dim, (uint64_t *)ctx->draws.p));
+        CU(launch_combine(ctx->lc(), f, (const int64_t *)ctx->draws.p, dim, 1, dim, d_out, d_out, nullptr, 0));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDA_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int sda_abi_version(void) { return SDA_B200_ABI_VERSION; }
+
+int sda_ctx_create(int device, sda_ctx **out) {
+    sda_ctx *ctx = nullptr;
+    if (!out) return fail(ctx, SDA_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ctx, SDA_ERR_CUDA, "no CUDA device available (%s): libsda_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    }
+    if (device < 0 || device >= ndev) return fail(ctx, SDA_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(ctx, SDA_ERR_CUDA, "device %d is sm_%d%d; libsda_b200 is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    sda_ctx *c = new sda_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    ctx = c;
+    cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaMalloc((void **)&c->d_flag, 2 * sizeof(unsigned));
+    if (err == cudaSuccess) err = cudaMallocHost((void **)&c->h_flag, 2 * sizeof(unsigned));
+    for (int i = 0; i < 4 && err == cudaSuccess; i++) err = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
+    if (err != cudaSuccess) {
+        g_create_error = std::string("CUDA error ") + cudaGetErrorString(err) + " while creating the context";
+        sda_ctx_destroy(c);
+        return SDA_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return SDA_OK;
+}
+
+void sda_ctx_destroy(sda_ctx *ctx) {
+    if (!ctx) return;
+    DeviceGuard g(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat}) b->release();
+    ctx->stage[0].release();
+    ctx->stage[1].release();
+    if (ctx->d_flag) cudaFree(ctx->d_flag);
+    if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    for (int i = 0; i < 4; i++)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char *sda_last_error(const sda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds) {
+    if (!ctx) return SDA_ERR_INVALID;
+    if (rounds != 8 && rounds != 12 && rounds != 20) return fail(ctx, SDA_ERR_INVALID, "rng rounds must be 8, 12 or 20");
+    ctx->rounds = rounds;
+    return SDA_OK;
+}
+int sda_ctx_get_rng_rounds(const sda_ctx *ctx) { return ctx ? ctx->rounds : 0; }
+int sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return SDA_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SDA_OK;
+}
+void *sda_ctx_get_stream(const sda_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int sda_ctx_synchronize(sda_ctx *ctx) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CU(cudaStreamSynchronize(ctx->stream));
+    return SDA_OK;
+}
+uint64_t sda_ctx_launch_count(const sda_ctx *ctx) { return ctx ? ctx->nlaunch : 0; }
+const char *sda_ctx_last_kernel(const sda_ctx *ctx) { return ctx ? ctx->kernel_name : ""; }
+
+int sda_host_alloc(sda_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return SDA_OK;
+}
+int sda_host_free(sda_ctx *ctx, void *ptr) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (ptr) CU(cudaFreeHost(ptr));
+    return SDA_OK;
+}
+
+// ---- derived scheme properties (protocol/src/crypto.rs:117-155) --------------------------------
+size_t sda_input_size(const sda_sharing_scheme *s) { return s->kind == SDA_SHARING_ADDITIVE ? 1 : (size_t)s->secret_count; }
+size_t sda_output_size(const sda_sharing_scheme *s) { return (size_t)s->share_count; }
+size_t sda_privacy_threshold(const sda_sharing_scheme *s) {
+    return s->kind == SDA_SHARING_ADDITIVE ? (size_t)s->share_count - 1 : (size_t)s->privacy_threshold;
+}
+size_t sda_reconstruction_threshold(const sda_sharing_scheme *s) {
+    return s->kind == SDA_SHARING_ADDITIVE ? (size_t)s->share_count : (size_t)(s->privacy_threshold + s->secret_count);
+}
+size_t sda_share_batches(const sda_sharing_scheme *s, size_t dim) {
+    const size_t k = sda_input_size(s);
+    return k ? (dim + k - 1) / k : 0;
+}
+size_t sda_mask_len(const sda_masking_scheme *s, size_t dim) {
+    switch (s->kind) {
+    case SDA_MASK_FULL: return dim;
+    case SDA_MASK_CHACHA: return (size_t)((s->seed_bitsize + 31) / 32);
+    default: return 0;
+    }
+}
+
+int sda_sharing_scheme_validate(sda_ctx *ctx, const sda_sharing_scheme *s) {
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (s->kind == SDA_SHARING_PACKED_SHAMIR) {
+        Matrix M;
+        OK(share_matrix(ctx, pk, &M));
+    }
+    return SDA_OK;
+}
+
+int sda_packed_share_matrix(sda_ctx *ctx, const sda_sharing_scheme *s, int64_t *out) {
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (s->kind != SDA_SHARING_PACKED_SHAMIR) return fail(ctx, SDA_ERR_INVALID, "not a PackedShamir scheme");
+    Matrix M;
+    OK(share_matrix(ctx, pk, &M));
+    for (int i = 0; i < M.rows * M.cols; i++) out[i] = (int64_t)M.e[i];
+    return SDA_OK;
+}
+
+int sda_packed_reconstruct_matrix(sda_ctx *ctx, const sda_sharing_scheme *s, const uint64_t *indices, size_t m,
+                                  int64_t *out) {
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (s->kind != SDA_SHARING_PACKED_SHAMIR) return fail(ctx, SDA_ERR_INVALID, "not a PackedShamir scheme");
+    Matrix R;
+    OK(reconstruct_matrix(ctx, pk, indices, m, &R));
+    for (int i = 0; i < R.rows * R.cols; i++) out[i] = (int64_t)R.e[i];
+    return SDA_OK;
+}
+
+// ---- device-pointer entry points -------------------------------------------------------------------
+
+int sda_share_generate_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t secrets_ld,
+                           size_t P, size_t dim, const uint8_t *seeds, int64_t *d_shares_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
+    return share_generate_core(ctx, s, d_secrets, secrets_ld, P, dim, seeds, d_shares_out);
+}
+
+int sda_share_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld, size_t P,
+                          size_t L, const int64_t *d_acc_in, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    if (ld < L) return fail(ctx, SDA_ERR_INVALID, "Wrong dimension");
+    return combine_core(ctx, s->modulus, d_shares, ld, P, L, d_acc_in, d_out);
+}
+
+int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets,
+                                   size_t secrets_ld, size_t P, size_t dim, const uint8_t *seeds,
+                                   const int64_t *d_acc_in, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
+    const size_t n = s->share_count, B = sda_share_batches(s, dim);
+    if (n * B == 0) return SDA_OK;
+    if (P == 0) {
+        if (d_acc_in && d_acc_in != d_out)
+            CU(cudaMemcpyAsync(d_out, d_acc_in, n * B * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        else if (!d_acc_in)
+            CU(cudaMemsetAsync(d_out, 0, n * B * sizeof(int64_t), ctx->stream));
+        return SDA_OK;
+    }
+    // tiles of participants: generate [tile][n][B] into ctx->aux, fold each clerk's rows into out
+    const size_t per = n * B * sizeof(int64_t);
+    size_t tile = std::max<size_t>(1, std::min<size_t>(P, (size_t(2) << 30) / per));
+    CU(ctx->aux.reserve(tile * per));
+    int64_t *d_tile = (int64_t *)ctx->aux.p;
+    const int64_t *acc = d_acc_in;
+    for (size_t p0 = 0; p0 < P; p0 += tile) {
+        const size_t pc = std::min(tile, P - p0);
+        OK(share_generate_core(ctx, s, d_secrets + p0 * secrets_ld, secrets_ld, pc, dim, seeds + 32 * p0, d_tile));
+        for (size_t r = 0; r < n; r++)
+            OK(combine_core(ctx, s->modulus, d_tile + r * B, n * B, pc, B, acc ? acc + r * B : nullptr, d_out + r * B));
+        acc = d_out;
+    }
+    return SDA_OK;
+}
+
+int sda_mod_reduce_dev(sda_ctx *ctx, int64_t modulus, const int64_t *d_in, size_t n, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
+    CU(launch_mod_reduce(ctx->lc(), make_field((uint64_t)modulus), d_in, n, d_out));
+    return SDA_OK;
+}
+
+int sda_mod_reduce_u64_dev(sda_ctx *ctx, int64_t modulus, const uint64_t *d_in, size_t n, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
+    CU(launch_mod_reduce(ctx->lc(), make_field((uint64_t)modulus), (const int64_t *)d_in, n, d_out, true));
+    return SDA_OK;
+}
+
+int sda_secret_reconstruct_dev(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                               const int64_t *d_shares, size_t ld, size_t m, size_t B, int64_t *d_secrets_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (ld < B) return fail(ctx, SDA_ERR_INVALID, "ld < B");
+    return reconstruct_core(ctx, s, dimension, indices, d_shares, ld, m, B, d_secrets_out, nullptr);
+}
+
+int sda_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secrets, size_t dim,
+                 const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (s && s->kind == SDA_MASK_CHACHA) {
+        int64_t words[8] = {0};
+        OK(mask_core(ctx, s, d_secrets, dim, rng_seed, nullptr, words, d_masked_out));
+        const size_t nw = sda_mask_len(s, dim);
+        if (nw && d_mask_out) {
+            CU(cudaMemcpyAsync(d_mask_out, words, nw * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        return SDA_OK;
+    }
+    return mask_core(ctx, s, d_secrets, dim, rng_seed, d_mask_out, nullptr, d_masked_out);
+}
+
+int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_masks, size_t P, size_t mask_len,
+                         int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
+    switch (s->kind) {
+    case SDA_MASK_NONE:
+        if (mask_len != 0) return fail(ctx, SDA_ERR_INVALID, "assertion failed: masks.iter().all(|mask| mask.len() == 0)");
+        return SDA_OK;
+    case SDA_MASK_FULL:
+        return combine_core(ctx, s->modulus, d_masks, mask_len, P, P ? mask_len : 0, nullptr, d_out);
+    default: {
+        std::vector<int64_t> h(P * mask_len);
+        if (!h.empty()) {
+            CU(cudaMemcpyAsync(h.data(), d_masks, h.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        return chacha_mask_combine_core(ctx, s, h.data(), P, mask_len, d_out);
+    }
+    }
+}
+
+int sda_unmask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_mask, const int64_t *d_masked,
+                   size_t dim, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
+    if (s->kind == SDA_MASK_NONE) {
+        if (dim && d_out != d_masked)
+            CU(cudaMemcpyAsync(d_out, d_masked, dim * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        return SDA_OK;
+    }
+    CU(launch_submod(ctx->lc(), make_field((uint64_t)s->modulus), d_masked, d_mask, dim, d_out));   // full.rs:60-63
+    return SDA_OK;
+}
+
+int sda_synth_fill_dev(sda_ctx *ctx, uint32_t stream, int64_t modulus, uint64_t start, size_t count, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
+    CU(launch_synth_fill(ctx->lc(), make_field((uint64_t)modulus), stream, start, count, d_out));
+    return SDA_OK;
+}
+
+// ---- host-pointer entry points ---------------------------------------------------------------------
+
+int sda_share_generate(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *secrets, size_t dim,
+                       const uint8_t rng_seed[32], int64_t *shares_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    const size_t n = s->share_count, B = sda_share_batches(s, dim);
+    if (dim == 0) return SDA_OK;
+    if (!secrets || !shares_out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    const size_t ldp = (dim + 3) & ~(size_t)3;
+    CU(ctx->in.reserve(ldp * sizeof(int64_t)));
+    CU(ctx->out.reserve(n * B * sizeof(int64_t)));
+    OK(h2d(ctx, ctx->in.p, secrets, dim * sizeof(int64_t)));
+    OK(share_generate_core(ctx, s, (const int64_t *)ctx->in.p, ldp, 1, dim, rng_seed, (int64_t *)ctx->out.p));
+    return d2h(ctx, shares_out, ctx->out.p, n * B * sizeof(int64_t));
+}
+
+// streamed combine of a host matrix: tiles of rows through ctx->in, running sum in ctx->out
+static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, const int64_t *const *rows, size_t P,
+                        size_t L, int64_t *out) {
+    if (L == 0) return SDA_OK;
+    const size_t ldp = (L + 3) & ~(size_t)3;
+    const size_t row_bytes = ldp * sizeof(int64_t);
+    const size_t tile = std::max<size_t>(1, std::min<size_t>(std::max<size_t>(P, 1), (size_t(1) << 30) / row_bytes));
+    CU(ctx->in.reserve(tile * row_bytes));
+    CU(ctx->out.reserve(row_bytes));
+    int64_t *d_in = (int64_t *)ctx->in.p, *d_acc = (int64_t *)ctx->out.p;
+    if (P == 0) CU(cudaMemsetAsync(d_acc, 0, row_bytes, ctx->stream));
+    for (size_t p0 = 0; p0 < P; p0 += tile) {
+        const size_t pc = std::min(tile, P - p0);
+        if (shares && ldp == L) {
+            OK(h2d(ctx, d_in, shares + p0 * L, pc * L * sizeof(int64_t)));
+        } else if (shares) {
+            CU(cudaMemcpy2DAsync(d_in, row_bytes, shares + p0 * L, L * sizeof(int64_t), L * sizeof(int64_t), pc,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            for (size_t p = 0; p < pc; p++)
+                OK(h2d(ctx, d_in + p * ldp, shares ? shares + (p0 + p) * L : rows[p0 + p], L * sizeof(int64_t)));
+        }
+        OK(combine_core(ctx, modulus, d_in, ldp, pc, L, p0 ? d_acc : nullptr, d_acc));
+    }
+    return d2h(ctx, out, d_acc, L * sizeof(int64_t));
+}
+
+int sda_share_combine(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *shares, size_t P, size_t L,
+                      int64_t *out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    if (P == 0 || L == 0) return SDA_OK;   // combiner.rs:17: dimension of an empty input is 0
+    if (!shares || !out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    return combine_host(ctx, s->modulus, shares, nullptr, P, L, out);
+}
+
+int sda_share_combine_rows(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *rows, const size_t *row_lens,
+                           size_t P, int64_t *out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    const size_t L = P ? row_lens[0] : 0;   // combiner.rs:17
+    if (out_len) *out_len = L;
+    for (size_t p = 0; p < P; p++)
+        if (row_lens[p] != L) return fail(ctx, SDA_ERR_INVALID, "Wrong dimension");   // combiner.rs:21
+    if (L == 0) return SDA_OK;
+    return combine_host(ctx, s->modulus, nullptr, rows, P, L, out);
+}
+
+static int reconstruct_host(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                            const int64_t *shares, const int64_t *const *rows, const size_t *row_lens, size_t m,
+                            size_t B, int64_t *secrets_out, size_t *out_len) {
+    OK(validate(ctx, s, nullptr));
+    if (s->kind == SDA_SHARING_ADDITIVE) {
+        // additive.rs:56-70
+        const size_t len = m ? (rows ? row_lens[0] : B) : 0;
+        if (out_len) *out_len = len;
+        if (rows)
+            for (size_t i = 0; i < m; i++)
+                if (row_lens[i] != len) return fail(ctx, SDA_ERR_INVALID, "Mismatching dimension");   // additive.rs:64
+        if (len == 0) return SDA_OK;
+        return combine_host(ctx, s->modulus, shares, rows, m, len, secrets_out);
+    }
+    const size_t k = s->secret_count;
+    const size_t nb = (dimension + k - 1) / k;
+    if (out_len) *out_len = dimension;
+    if (nb == 0) return SDA_OK;
+    if (m < sda_reconstruction_threshold(s)) return fail(ctx, SDA_ERR_INVALID, "Not enough shares to reconstruct");
+    size_t minlen = B;
+    if (rows) {
+        minlen = (size_t)-1;
+        for (size_t i = 0; i < m; i++) minlen = std::min(minlen, row_lens[i]);
+    }
+    if (minlen < nb)
+        return fail(ctx, SDA_ERR_INVALID, "index out of bounds: the len is %zu but the index is %zu", minlen, minlen);
+    const size_t ldp = (nb + 3) & ~(size_t)3;
+    CU(ctx->in.reserve(m * ldp * sizeof(int64_t)));
+    for (size_t i = 0; i < m; i++)
+        OK(h2d(ctx, (int64_t *)ctx->in.p + i * ldp, rows ? rows[i] : shares + i * B, nb * sizeof(int64_t)));
+    CU(ctx->out.reserve(dimension * sizeof(int64_t)));
+    OK(reconstruct_core(ctx, s, dimension, indices, (const int64_t *)ctx->in.p, ldp, m, nb, (int64_t *)ctx->out.p, nullptr));
+    return d2h(ctx, secrets_out, ctx->out.p, dimension * sizeof(int64_t));
+}
+
+int sda_secret_reconstruct(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                           const int64_t *shares, size_t m, size_t B, int64_t *secrets_out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    return reconstruct_host(ctx, s, dimension, indices, shares, nullptr, nullptr, m, B, secrets_out, out_len);
+}
+
+int sda_secret_reconstruct_rows(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension, const uint64_t *indices,
+                                const int64_t *const *rows, const size_t *row_lens, size_t m, int64_t *secrets_out,
+                                size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    return reconstruct_host(ctx, s, dimension, indices, nullptr, rows, row_lens, m, 0, secrets_out, out_len);
+}
+
+int sda_mask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *secrets, size_t dim, const uint8_t rng_seed[32],
+             int64_t *mask_out, size_t *mask_len, int64_t *masked_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
+    const size_t ml = sda_mask_len(s, dim);
+    if (mask_len) *mask_len = ml;
+    if (s->kind == SDA_MASK_CHACHA && s->dimension != dim)
+        return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (chacha.rs:26: scheme dimension %llu, %zu secrets)",
+                    (unsigned long long)s->dimension, dim);
+    const size_t bytes = dim * sizeof(int64_t);
+    CU(ctx->in.reserve(std::max<size_t>(bytes, 8)));
+    CU(ctx->out.reserve(std::max<size_t>(bytes, 8)));
+    CU(ctx->aux.reserve(std::max<size_t>(bytes, 8)));
+    OK(h2d(ctx, ctx->in.p, secrets, bytes));
+    int64_t words[8] = {0};
+    OK(mask_core(ctx, s, (const int64_t *)ctx->in.p, dim, rng_seed, (int64_t *)ctx->aux.p, words, (int64_t *)ctx->out.p));
+    if (s->kind == SDA_MASK_FULL) OK(d2h(ctx, mask_out, ctx->aux.p, bytes));
+    if (s->kind == SDA_MASK_CHACHA)
+        for (size_t i = 0; i < ml; i++) mask_out[i] = words[i];
+    return d2h(ctx, masked_out, ctx->out.p, bytes);
+}
+
+int sda_mask_combine(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *masks, size_t P, size_t mask_len,
+                     int64_t *out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
+    switch (s->kind) {
+    case SDA_MASK_NONE:   // none.rs:22-25
+        if (mask_len != 0) return fail(ctx, SDA_ERR_INVALID, "assertion failed: masks.iter().all(|mask| mask.len() == 0)");
+        if (out_len) *out_len = 0;
+        return SDA_OK;
+    case SDA_MASK_FULL: {   // full.rs:38-51
+        const size_t L = P ? mask_len : 0;
+        if (out_len) *out_len = L;
+        if (L == 0) return SDA_OK;
+        return combine_host(ctx, s->modulus, masks, nullptr, P, L, out);
+    }
+    default: {   // chacha.rs:57-76
+        const size_t dim = (size_t)s->dimension;
+        if (out_len) *out_len = dim;
+        if (dim == 0) return SDA_OK;
+        CU(ctx->out.reserve(dim * sizeof(int64_t)));
+        OK(chacha_mask_combine_core(ctx, s, masks, P, mask_len, (int64_t *)ctx->out.p));
+        return d2h(ctx, out, ctx->out.p, dim * sizeof(int64_t));
+    }
+    }
+}
+
+int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, size_t mask_len, const int64_t *masked,
+               size_t dim, int64_t *out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
+    if (s->kind == SDA_MASK_NONE) {   // none.rs:29-32
+        if (mask_len != 0) return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (none.rs:30)");
+        if (dim) memmove(out, masked, dim * sizeof(int64_t));
+        return SDA_OK;
+    }
+    if (mask_len != dim)   // full.rs:58, chacha.rs:83
+        return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (full.rs:58 / chacha.rs:83: mask %zu, masked %zu)",
+                    mask_len, dim);
+    if (dim == 0) return SDA_OK;
+    const size_t bytes = dim * sizeof(int64_t);
+    CU(ctx->in.reserve(bytes));
+    CU(ctx->aux.reserve(bytes));
+    CU(ctx->out.reserve(bytes));
+    OK(h2d(ctx, ctx->in.p, masked, bytes));
+    OK(h2d(ctx, ctx->aux.p, mask, bytes));
+    CU(launch_submod(ctx->lc(), make_field((uint64_t)s->modulus), (const int64_t *)ctx->in.p, (const int64_t *)ctx->aux.p,
+                     dim, (int64_t *)ctx->out.p));
+    return d2h(ctx, out, ctx->out.p, bytes);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

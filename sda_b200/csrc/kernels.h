@@ -1,0 +1,93 @@
+// kernels.h -- internal launch interface between the C-ABI host layer (api.cu) and the
+// sm_100a kernels.  Every launcher enqueues on `stream`, never synchronises, bumps *nlaunch
+// once per kernel launched and returns the launch status.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "chacha.cuh"
+#include "field.cuh"
+
+namespace sda {
+
+constexpr int MAX_W = 16;   // k + t   (columns of the share matrix)
+constexpr int MAX_N = 32;   // share_count (rows of the share matrix / columns of R)
+constexpr int MAX_K = 16;   // secret_count (rows of R)
+
+// n x w share matrix (or k x m' reconstruction matrix), canonical entries, row-major
+struct Matrix {
+    uint64_t e[MAX_N * MAX_W];
+    int rows, cols;
+};
+
+struct LaunchCtx {
+    cudaStream_t stream;
+    uint64_t *nlaunch;
+    int sm_count;
+    const char **kernel_name;   // variant label of the last sharing launch
+};
+
+// ---- K3: column-wise modular sums -------------------------------------------------------
+// out[i] = (sum_p rows[p*ld + i] + acc_in[i]) mod m, canonical.  `scratch` (>= scratch_elems
+// i64) holds per-slice partial sums when the participant axis is split across CTAs.
+cudaError_t launch_combine(const LaunchCtx &lc, const FieldParams &f, const int64_t *rows, size_t ld, size_t P,
+                           size_t L, const int64_t *acc_in, int64_t *out, int64_t *scratch, size_t scratch_elems);
+size_t combine_scratch_elems(int sm_count, size_t P, size_t L);
+
+// out[i] = in[i] mod m (canonical)
+cudaError_t launch_mod_reduce(const LaunchCtx &lc, const FieldParams &f, const int64_t *in, size_t n, int64_t *out,
+                              bool input_unsigned = false);
+// out[i] = (a[i] - b[i]) mod m  (unmask, full.rs:60-63)
+cudaError_t launch_submod(const LaunchCtx &lc, const FieldParams &f, const int64_t *a, const int64_t *b, size_t n,
+                          int64_t *out);
+
+// ---- K1: additive split / masks ---------------------------------------------------------
+// flag[0] |= 1 when some draw was rejected by gen_range (caller then uses the exact path).
+// shares_out[P][n][dim]; keys[P] device array.  draws != nullptr: read pre-drawn canonical
+// samples draws[p][dim*(n-1)] instead of generating them (exact path).
+cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
+                                  int n, const int64_t *secrets, size_t ld, size_t P, size_t dim,
+                                  const ChaChaKey *keys, const uint64_t *draws, int64_t *shares_out,
+                                  unsigned *flag);
+// mask_out (may be null) [dim], masked_out [dim]: Full mask (full.rs:24-31) and the
+// participant side of the ChaCha mask (chacha.rs:36-45)
+cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
+                        const int64_t *secrets, size_t dim, const ChaChaKey &key, const uint64_t *draws,
+                        int64_t *mask_out, int64_t *masked_out, unsigned *flag);
+// ChaCha mask re-expansion (chacha.rs:60-73): out[i] = sum_p draw_p(i) mod m over P keys
+cudaError_t launch_chacha_mask_combine(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr,
+                                       const ChaChaKey *keys, size_t P, size_t dim, int64_t *out,
+                                       int64_t *scratch, size_t scratch_elems, unsigned *flag);
+size_t chacha_mask_combine_scratch_elems(int sm_count, size_t P, size_t dim);
+
+// exact gen_range stream: out[0..count) = first `count` accepted samples of the key's stream.
+// Needs scratch of draw_exact_scratch_elems(count) u64.  Device-side only, no host sync:
+// *status (device) gets 1 if the provisioned stream window was too short (caller retries
+// with a larger `window`).
+cudaError_t launch_draw_exact(const LaunchCtx &lc, const DrawParams &dr, int rounds, const ChaChaKey &key,
+                              size_t count, size_t window, uint64_t *out, uint64_t *scratch, unsigned *status);
+size_t draw_exact_scratch_elems(size_t window);
+
+// ---- K2: packed-Shamir share generation ---------------------------------------------------
+// shares_out[P][n][B], B = ceil(dim/k).  Mtx is n x (k+t); d_mat is its device copy (row-major
+// u64), needed only with draws != nullptr.
+cudaError_t launch_packed_share(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k,
+                                int t, int n, const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P,
+                                size_t dim, const ChaChaKey *keys, const uint64_t *draws, const uint64_t *d_mat,
+                                int64_t *shares_out, unsigned *flag);
+// true when launch_packed_share / launch_additive_split have an in-kernel-rng instantiation
+bool packed_share_has_fast_path(int k, int t, int n);
+bool additive_split_has_fast_path(int n);
+
+// ---- reveal: secrets = R . shares ------------------------------------------------------------
+// shares[m][ld] -> secrets_out[dimension]; R is k x m.
+cudaError_t launch_packed_reconstruct(const LaunchCtx &lc, const FieldParams &f, int k, int m, const Matrix &R,
+                                      const int64_t *shares, size_t ld, size_t dimension, int64_t *secrets_out);
+
+// ---- synthetic inputs ---------------------------------------------------------------------
+cudaError_t launch_synth_fill(const LaunchCtx &lc, const FieldParams &f, uint32_t stream_id, uint64_t start,
+                              size_t count, int64_t *out);
+
+}  // namespace sda

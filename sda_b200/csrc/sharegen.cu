@@ -1,0 +1,566 @@
+// sharegen.cu -- K1 (additive split, Full / ChaCha masks) and K2 (packed-Shamir share
+// generation): the participant side of the hot path.
+//
+//   additive split   client/src/crypto/sharing/additive.rs:32-51  (+ batched.rs:18-53)
+//   packed Shamir    client/src/crypto/sharing/packed_shamir.rs:40-43 -> tss 0.2 `share`
+//                    (+ batched.rs:18-53: zero-padded last batch, clerk-major scatter)
+//   Full mask        client/src/crypto/masking/full.rs:21-35
+//   ChaCha mask      client/src/crypto/masking/chacha.rs:24-54 (participant), :56-77 (recipient)
+//
+// Randomness never touches HBM: draw q of a participant's stream is the q-th u64 of
+// ChaCha(key, rounds) (rand-0.3 word order) and a thread owns whole 64-byte keystream blocks
+// = 8 draws.  A thread therefore processes a *unit* of G = 8/gcd(d,8) consecutive elements
+// (d = draws per element: n-1 for additive, t for packed, 1 for masks), which makes its
+// input a contiguous run of G*k i64 and its output n contiguous runs of G i64.
+// gen_range's rejection (probability ~2^-60 for the supported moduli) shifts the whole
+// stream, so a rejected word raises `flag` and the host redoes the call on the exact path
+// (draws pre-computed by draw_exact into scratch, kernels instantiated with FROM_MEM).
+#include "kernels.h"
+#include "vecio.cuh"
+
+namespace sda {
+
+namespace {
+
+constexpr int CTA = 128;
+
+constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
+template <int D>
+struct Unit {
+    static constexpr int G = 8 / gcd_c(D, 8);    // elements (batches) per thread
+    static constexpr int NB = D * G / 8;         // keystream blocks per thread
+};
+
+__device__ __forceinline__ ChaChaKey load_key(const ChaChaKey *keys, size_t p) {
+    ChaChaKey k;
+    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
+    uint4 a = __ldg(src), b = __ldg(src + 1);
+    k.w[0] = a.x; k.w[1] = a.y; k.w[2] = a.z; k.w[3] = a.w;
+    k.w[4] = b.x; k.w[5] = b.y; k.w[6] = b.z; k.w[7] = b.w;
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------
+// additive split, D = n - 1 draws per element, in-kernel randomness
+// ------------------------------------------------------------------------------------------
+template <bool M61, uint32_t DK, int ROUNDS, int D>
+__global__ void __launch_bounds__(CTA)
+additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, const ChaChaKey *__restrict__ keys,
+                      int64_t *__restrict__ out, FieldParams f, DrawParams dr, int in_lanes, int out_lanes,
+                      unsigned *flag) {
+    constexpr int G = Unit<D>::G, NB = Unit<D>::NB;
+    const size_t p = blockIdx.y;
+    const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t e0 = u * G;
+    if (e0 >= dim) return;
+    const int nvalid = (int)min((size_t)G, dim - e0);
+    const ChaChaKey key = load_key(keys, p);
+
+    int64_t x[G];
+    load_run<G>(secrets + p * ld + e0, x, nvalid, in_lanes);
+
+    int64_t sh[D + 1][G];
+    uint64_t blk[8];
+    bool rej = false;
+#pragma unroll
+    for (int e = 0; e < G; e++) {
+        uint64_t acc = canon<M61>(f, x[e]);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const int q = e * D + j;
+            if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
+            bool r;
+            const uint64_t s = draw_reduce<DK>(dr, blk[q % 8], r);
+            rej |= r && e < nvalid;
+            sh[j][e] = (int64_t)s;                      // additive.rs:42-44
+            acc = submod(acc, s, f.m);                  // additive.rs:47
+        }
+        sh[D][e] = (int64_t)acc;
+    }
+    int64_t *o = out + (p * (D + 1)) * dim + e0;
+#pragma unroll
+    for (int j = 0; j <= D; j++) store_run<G>(o + (size_t)j * dim, sh[j], nvalid, out_lanes);
+    if (rej) atomicOr(flag, 1u);
+}
+
+// any n, draws read from memory (exact path and n - 1 > 4): one element per thread
+template <bool M61>
+__global__ void __launch_bounds__(CTA)
+additive_split_mem_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, int n,
+                          const uint64_t *__restrict__ draws, int64_t *__restrict__ out, FieldParams f) {
+    const size_t p = blockIdx.y;
+    const size_t e = (size_t)blockIdx.x * CTA + threadIdx.x;
+    if (e >= dim) return;
+    uint64_t acc = canon<M61>(f, secrets[p * ld + e]);
+    const uint64_t *d = draws + (p * dim + e) * (size_t)(n - 1);
+    int64_t *o = out + p * (size_t)n * dim + e;
+    for (int j = 0; j < n - 1; j++) {
+        const uint64_t s = d[j];
+        o[(size_t)j * dim] = (int64_t)s;
+        acc = submod(acc, s, f.m);
+    }
+    o[(size_t)(n - 1) * dim] = (int64_t)acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// masks: one draw per element
+// ------------------------------------------------------------------------------------------
+template <bool M61, uint32_t DK, int ROUNDS, bool FROM_MEM>
+__global__ void __launch_bounds__(CTA)
+mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, const uint64_t *__restrict__ draws,
+            int64_t *__restrict__ mask_out, int64_t *__restrict__ masked_out, FieldParams f, DrawParams dr,
+            int lanes, unsigned *flag) {
+    constexpr int G = 8;
+    const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t e0 = u * G;
+    if (e0 >= dim) return;
+    const int nvalid = (int)min((size_t)G, dim - e0);
+    int64_t x[G], mk[G], md[G];
+    load_run<G>(secrets + e0, x, nvalid, lanes);
+    uint64_t blk[8];
+    bool rej = false;
+    if (FROM_MEM) {
+#pragma unroll
+        for (int e = 0; e < G; e++) blk[e] = e < nvalid ? draws[e0 + e] : 0;
+    } else {
+        chacha_draws8<ROUNDS>(key, u, blk);
+    }
+#pragma unroll
+    for (int e = 0; e < G; e++) {
+        uint64_t s;
+        if (FROM_MEM) {
+            s = blk[e];
+        } else {
+            bool r;
+            s = draw_reduce<DK>(dr, blk[e], r);
+            rej |= r && e < nvalid;
+        }
+        mk[e] = (int64_t)s;                                            // full.rs:24-27
+        md[e] = (int64_t)addmod(canon<M61>(f, x[e]), s, f.m);          // full.rs:28-31
+    }
+    if (mask_out != nullptr) store_run<G>(mask_out + e0, mk, nvalid, lanes);
+    store_run<G>(masked_out + e0, md, nvalid, lanes);
+    if (!FROM_MEM && rej) atomicOr(flag, 1u);
+}
+
+// recipient-side ChaCha mask combine (chacha.rs:60-73): sum over P seeds of the re-expanded
+// masks.  Compute-bound by construction (P keystream blocks per 8 outputs, no input traffic).
+// grid.y slices the seed axis; slice partials (canonical) go to out + slice*out_ld.
+template <bool M61, uint32_t DK>
+__global__ void __launch_bounds__(CTA)
+chacha_mask_combine_kernel(const ChaChaKey *__restrict__ keys, size_t P, size_t seeds_per_slice, size_t dim,
+                           int64_t *__restrict__ out, size_t out_ld, FieldParams f, DrawParams dr, int lanes,
+                           unsigned *flag) {
+    constexpr int G = 8;
+    const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t e0 = u * G;
+    if (e0 >= dim) return;
+    const int nvalid = (int)min((size_t)G, dim - e0);
+    const size_t p0 = (size_t)blockIdx.y * seeds_per_slice;
+    const size_t p1 = min(P, p0 + seeds_per_slice);
+    uint64_t acc[G];
+#pragma unroll
+    for (int e = 0; e < G; e++) acc[e] = 0;
+    bool rej = false;
+    for (size_t p = p0; p < p1; p++) {
+        const ChaChaKey key = load_key(keys, p);
+        uint64_t blk[8];
+        chacha_draws8<20>(key, u, blk);
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            bool r;
+            const uint64_t s = draw_reduce<DK>(dr, blk[e], r);
+            rej |= r && e < nvalid;
+            acc[e] = addmod(acc[e], s, f.m);
+        }
+    }
+    int64_t r[G];
+#pragma unroll
+    for (int e = 0; e < G; e++) r[e] = (int64_t)acc[e];
+    store_run<G>(out + (size_t)blockIdx.y * out_ld + e0, r, nvalid, lanes);
+    if (rej) atomicOr(flag, 1u);
+}
+
+// ------------------------------------------------------------------------------------------
+// packed Shamir: shares = M . [secrets ; randomness] per batch
+// ------------------------------------------------------------------------------------------
+template <int N, int W>
+struct MatSplit {            // canonical entries split at bit 32 (Mersenne path) / whole (generic)
+    uint32_t lo[N * W];
+    uint32_t hi[N * W];
+};
+
+// Mersenne-61 dot product of W terms, lazily accumulated in four 64-bit partial sums:
+//   M = m0 + m1 2^32 (m1 < 2^29),  x = x0 + x1 2^32 (x1 < 2^29)
+//   LL = sum m0 x0 (carry counted), LH = sum m0 x1, HL = sum m1 x0 (< 8 2^61), HH = sum m1 x1 (< 8 2^58)
+//   value = LL + (LH + HL) 2^32 + HH 2^64, folded with 2^61 == 1; at most 8 terms per fold.
+template <int N, int W>
+__device__ __forceinline__ uint64_t dot_m61(const MatSplit<N, W> &m, int j, const uint32_t (&x0)[W],
+                                            const uint32_t (&x1)[W]) {
+    const uint64_t M29 = (1ull << 29) - 1;
+    uint64_t s = 0;
+#pragma unroll
+    for (int c = 0; c < W; c += 8) {
+        uint64_t LL = 0, LH = 0, HL = 0, HH = 0;
+        uint32_t LLc = 0;
+#pragma unroll
+        for (int i = c; i < (c + 8 < W ? c + 8 : W); i++) {
+            const uint32_t m0 = m.lo[j * W + i], m1 = m.hi[j * W + i];
+            const uint64_t t = (uint64_t)m0 * x0[i];
+            LL += t;
+            LLc += LL < t;
+            LH += (uint64_t)m0 * x1[i];
+            HL += (uint64_t)m1 * x0[i];
+            HH += (uint64_t)m1 * x1[i];
+        }
+        // y 2^32 == (y >> 29) + ((y & (2^29-1)) << 32)  for y < 2^64;   every piece < 2^62
+        s += (LL & P61) + (LL >> 61) + ((uint64_t)LLc << 3);
+        s += (LH >> 29) + (HL >> 29) + (((LH & M29) + (HL & M29)) << 32);
+        s += ((HH << 3) & P61) + (HH >> 58);
+        s = (s & P61) + (s >> 61);
+    }
+    return s >= P61 ? s - P61 : s;
+}
+
+// generic field: 128-bit accumulation, folded every `lazy` terms (lazy * (m-1)^2 + m < m 2^64)
+template <int N, int W>
+__device__ __forceinline__ uint64_t dot_generic(const FieldParams &f, int lazy, const MatSplit<N, W> &m, int j,
+                                                const uint64_t (&x)[W]) {
+    uint64_t lo = 0, hi = 0;
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint64_t a = ((uint64_t)m.hi[j * W + i] << 32) | m.lo[j * W + i];
+        const uint64_t pl = a * x[i], ph = __umul64hi(a, x[i]);
+        lo += pl;
+        hi += ph + (lo < pl);
+        if (++cnt == lazy && i + 1 < W) {
+            lo = reduce128_generic(f, hi, lo);
+            hi = 0;
+            cnt = 0;
+        }
+    }
+    return reduce128_generic(f, hi, lo);
+}
+
+template <int K, int T, int N, bool M61, uint32_t DK, int ROUNDS>
+__global__ void __launch_bounds__(CTA)
+packed_share_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B,
+                    const ChaChaKey *__restrict__ keys, int64_t *__restrict__ out, FieldParams f, DrawParams dr,
+                    int lazy, MatSplit<N, K + T> mat, int in_lanes, int out_lanes, unsigned *flag) {
+    constexpr int W = K + T;
+    constexpr int G = Unit<T>::G, NB = Unit<T>::NB;
+    const size_t p = blockIdx.y;
+    const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t b0 = u * G;
+    if (b0 >= B) return;
+    const int nb = (int)min((size_t)G, B - b0);
+    const ChaChaKey key = load_key(keys, p);
+
+    // contiguous run of G*K secrets; the last batch is zero padded (batched.rs:38-43)
+    int64_t s[G * K];
+    const size_t s0 = b0 * K;
+    const size_t avail = dim - s0;
+    load_run<G * K>(secrets + p * ld + s0, s, (int)min((size_t)(G * K), avail), in_lanes);
+
+    int64_t sh[N][G];
+    uint64_t blk[8];
+    bool rej = false;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        uint64_t x[W];
+#pragma unroll
+        for (int i = 0; i < K; i++) x[i] = canon<M61>(f, s[g * K + i]);
+#pragma unroll
+        for (int i = 0; i < T; i++) {
+            const int q = g * T + i;
+            if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
+            bool r;
+            x[K + i] = draw_reduce<DK>(dr, blk[q % 8], r);   // tss share(): Range::new(0, prime - 1)
+            rej |= r && g < nb;
+        }
+        if (M61) {
+            uint32_t x0[W], x1[W];
+#pragma unroll
+            for (int i = 0; i < W; i++) {
+                x0[i] = (uint32_t)x[i];
+                x1[i] = (uint32_t)(x[i] >> 32);
+            }
+#pragma unroll
+            for (int j = 0; j < N; j++) sh[j][g] = (int64_t)dot_m61<N, W>(mat, j, x0, x1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < N; j++) sh[j][g] = (int64_t)dot_generic<N, W>(f, lazy, mat, j, x);
+        }
+    }
+    int64_t *o = out + (p * N) * B + b0;
+#pragma unroll
+    for (int j = 0; j < N; j++) store_run<G>(o + (size_t)j * B, sh[j], nb, out_lanes);
+    if (rej) atomicOr(flag, 1u);
+}
+
+// any (k, t, n): one batch per thread, matrix in shared memory, draws from memory
+template <bool M61>
+__global__ void __launch_bounds__(CTA)
+packed_share_mem_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, int k, int t, int n,
+                        const uint64_t *__restrict__ mat_g, const uint64_t *__restrict__ draws,
+                        int64_t *__restrict__ out, FieldParams f, int lazy) {
+    __shared__ uint64_t mat[MAX_N * MAX_W];
+    const int w = k + t;
+    for (int i = threadIdx.x; i < n * w; i += CTA) mat[i] = mat_g[i];
+    __syncthreads();
+    const size_t p = blockIdx.y;
+    const size_t b = (size_t)blockIdx.x * CTA + threadIdx.x;
+    if (b >= B) return;
+    uint64_t x[MAX_W];
+    for (int i = 0; i < k; i++) {
+        const size_t e = b * k + i;
+        x[i] = e < dim ? canon<M61>(f, secrets[p * ld + e]) : 0;
+    }
+    const uint64_t *d = draws + (p * B + b) * (size_t)t;
+    for (int i = 0; i < t; i++) x[k + i] = d[i];
+    for (int j = 0; j < n; j++) {
+        uint64_t lo = 0, hi = 0;
+        int cnt = 0;
+        for (int i = 0; i < w; i++) {
+            const uint64_t a = mat[j * w + i];
+            const uint64_t pl = a * x[i], ph = __umul64hi(a, x[i]);
+            lo += pl;
+            hi += ph + (lo < pl);
+            if (++cnt == lazy) {
+                lo = reduce128_generic(f, hi, lo);
+                hi = 0;
+                cnt = 0;
+            }
+        }
+        out[(p * n + j) * B + b] = (int64_t)reduce128_generic(f, hi, lo);
+    }
+}
+
+// ---- host-side dispatch -------------------------------------------------------------------
+
+template <int N, int W>
+MatSplit<N, W> split_matrix(const Matrix &m) {
+    MatSplit<N, W> s;
+    for (int i = 0; i < N * W; i++) {
+        s.lo[i] = (uint32_t)m.e[i];
+        s.hi[i] = (uint32_t)(m.e[i] >> 32);
+    }
+    return s;
+}
+
+template <int K, int T, int N, bool M61, uint32_t DK, int ROUNDS>
+cudaError_t packed_launch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int lazy,
+                          const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P, size_t dim,
+                          const ChaChaKey *keys, int64_t *out, unsigned *flag) {
+    constexpr int G = Unit<T>::G;
+    const size_t B = (dim + K - 1) / K;
+    const size_t units = (B + G - 1) / G;
+    dim3 grid((unsigned)((units + CTA - 1) / CTA), (unsigned)P);
+    const int in_lanes = pick_lanes(secrets, ld, G * K);
+    const int out_lanes = pick_lanes(out, B, G);
+    packed_share_kernel<K, T, N, M61, DK, ROUNDS><<<grid, CTA, 0, lc.stream>>>(
+        secrets, ld, dim, B, keys, out, f, dr, lazy, split_matrix<N, K + T>(mtx), in_lanes, out_lanes, flag);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+template <int K, int T, int N>
+cudaError_t packed_dispatch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int lazy,
+                            const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P, size_t dim,
+                            const ChaChaKey *keys, int64_t *out, unsigned *flag) {
+#define SDA_PL(M61, DK, R) \
+    return packed_launch<K, T, N, M61, DK, R>(lc, f, dr, lazy, mtx, secrets, ld, P, dim, keys, out, flag)
+    if (f.kind == FIELD_MERSENNE61) {
+        if (rounds == 8) SDA_PL(true, DRAW_M61_MINUS1, 8);
+        if (rounds == 12) SDA_PL(true, DRAW_M61_MINUS1, 12);
+        SDA_PL(true, DRAW_M61_MINUS1, 20);
+    }
+    if (rounds == 8) SDA_PL(false, DRAW_GENERIC, 8);
+    if (rounds == 12) SDA_PL(false, DRAW_GENERIC, 12);
+    SDA_PL(false, DRAW_GENERIC, 20);
+#undef SDA_PL
+}
+
+template <bool M61, uint32_t DK, int ROUNDS, int D>
+cudaError_t additive_launch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, const int64_t *secrets,
+                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, int64_t *out, unsigned *flag) {
+    constexpr int G = Unit<D>::G;
+    const size_t units = (dim + G - 1) / G;
+    dim3 grid((unsigned)((units + CTA - 1) / CTA), (unsigned)P);
+    const int in_lanes = pick_lanes(secrets, ld, G);
+    const int out_lanes = pick_lanes(out, dim, G);
+    additive_split_kernel<M61, DK, ROUNDS, D><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, keys, out, f, dr,
+                                                                            in_lanes, out_lanes, flag);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+template <int D>
+cudaError_t additive_dispatch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
+                              const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                              int64_t *out, unsigned *flag) {
+#define SDA_AL(M61, DK, R) return additive_launch<M61, DK, R, D>(lc, f, dr, secrets, ld, P, dim, keys, out, flag)
+    if (f.kind == FIELD_MERSENNE61) {
+        if (rounds == 8) SDA_AL(true, DRAW_M61, 8);
+        if (rounds == 12) SDA_AL(true, DRAW_M61, 12);
+        SDA_AL(true, DRAW_M61, 20);
+    }
+    if (rounds == 8) SDA_AL(false, DRAW_GENERIC, 8);
+    if (rounds == 12) SDA_AL(false, DRAW_GENERIC, 12);
+    SDA_AL(false, DRAW_GENERIC, 20);
+#undef SDA_AL
+}
+
+// largest number of (m-1)^2 products that can be summed on top of a residue before the
+// 128-bit accumulator's high word reaches m
+int lazy_terms(uint64_t m) {
+    unsigned __int128 cap = ((unsigned __int128)m << 64) - m;
+    unsigned __int128 sq = (unsigned __int128)(m - 1) * (m - 1);
+    if (sq == 0) return 1 << 20;
+    unsigned __int128 q = cap / sq;
+    if (q > (1u << 20)) q = 1u << 20;
+    return q ? (int)q : 1;
+}
+
+}  // namespace
+
+bool packed_share_has_fast_path(int k, int t, int n) {
+    return (k == 3 && t == 2 && n == 5) || (k == 5 && t == 4 && n == 9) || (k == 3 && t == 4 && n == 7) ||
+           (k == 3 && t == 4 && n == 8);
+}
+bool additive_split_has_fast_path(int n) { return n >= 2 && n <= 5; }
+
+cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int n,
+                                  const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                                  const uint64_t *draws, int64_t *shares_out, unsigned *flag) {
+    if (dim == 0 || P == 0) return cudaSuccess;
+    if (P > 65535) return cudaErrorInvalidValue;
+    if (draws == nullptr && n >= 2 && n <= 5) {
+        *lc.kernel_name = f.kind == FIELD_MERSENNE61 ? "additive_split<in-kernel rng>/mersenne61"
+                                                     : "additive_split<in-kernel rng>/generic";
+        switch (n - 1) {
+        case 1: return additive_dispatch<1>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
+        case 2: return additive_dispatch<2>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
+        case 3: return additive_dispatch<3>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
+        case 4: return additive_dispatch<4>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
+        }
+    }
+    if (draws == nullptr && n > 1) return cudaErrorInvalidValue;   // caller must pre-draw
+    *lc.kernel_name = "additive_split<draws from memory>";
+    dim3 grid((unsigned)((dim + CTA - 1) / CTA), (unsigned)P);
+    if (f.kind == FIELD_MERSENNE61)
+        additive_split_mem_kernel<true><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, n, draws, shares_out, f);
+    else
+        additive_split_mem_kernel<false><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, n, draws, shares_out, f);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
+                        const int64_t *secrets, size_t dim, const ChaChaKey &key, const uint64_t *draws,
+                        int64_t *mask_out, int64_t *masked_out, unsigned *flag) {
+    if (dim == 0) return cudaSuccess;
+    const size_t units = (dim + 7) / 8;
+    const unsigned grid = (unsigned)((units + CTA - 1) / CTA);
+    int lanes = pick_lanes(secrets, 4, 8);
+    const int l2 = pick_lanes(masked_out, 4, 8), l3 = mask_out ? pick_lanes(mask_out, 4, 8) : 4;
+    if (l2 < lanes) lanes = l2;
+    if (l3 < lanes) lanes = l3;
+#define SDA_ML(M61, DK, R, MEM)                                                                               \
+    mask_kernel<M61, DK, R, MEM><<<grid, CTA, 0, lc.stream>>>(secrets, dim, key, draws, mask_out, masked_out, f, \
+                                                              dr, lanes, flag)
+    const bool m61 = f.kind == FIELD_MERSENNE61;
+    if (draws != nullptr) {
+        if (m61) SDA_ML(true, DRAW_M61, 20, true);
+        else SDA_ML(false, DRAW_GENERIC, 20, true);
+    } else if (m61) {
+        if (rounds == 8) SDA_ML(true, DRAW_M61, 8, false);
+        else if (rounds == 12) SDA_ML(true, DRAW_M61, 12, false);
+        else SDA_ML(true, DRAW_M61, 20, false);
+    } else {
+        if (rounds == 8) SDA_ML(false, DRAW_GENERIC, 8, false);
+        else if (rounds == 12) SDA_ML(false, DRAW_GENERIC, 12, false);
+        else SDA_ML(false, DRAW_GENERIC, 20, false);
+    }
+#undef SDA_ML
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+static size_t mask_combine_slices(int sm_count, size_t P, size_t dim) {
+    const size_t ctas = (((dim + 7) / 8) + CTA - 1) / CTA;
+    const size_t want = (size_t)sm_count * 8;
+    if (ctas >= want || P < 4) return 1;
+    size_t s = (want + ctas - 1) / ctas;
+    if (s > P / 2) s = P / 2;
+    if (s > 65535) s = 65535;
+    return s ? s : 1;
+}
+size_t chacha_mask_combine_scratch_elems(int sm_count, size_t P, size_t dim) {
+    const size_t s = mask_combine_slices(sm_count, P, dim);
+    return s > 1 ? s * ((dim + 3) & ~(size_t)3) : 0;
+}
+
+cudaError_t launch_chacha_mask_combine(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr,
+                                       const ChaChaKey *keys, size_t P, size_t dim, int64_t *out, int64_t *scratch,
+                                       size_t scratch_elems, unsigned *flag) {
+    if (dim == 0) return cudaSuccess;
+    const size_t dimp = (dim + 3) & ~(size_t)3;
+    size_t slices = mask_combine_slices(lc.sm_count, P, dim);
+    if (slices > 1 && (scratch == nullptr || scratch_elems < slices * dimp)) slices = 1;
+    const size_t sps = P ? (P + slices - 1) / slices : 1;
+    int64_t *dst = slices > 1 ? scratch : out;
+    const size_t units = (dim + 7) / 8;
+    dim3 grid((unsigned)((units + CTA - 1) / CTA), (unsigned)slices);
+    const int lanes = pick_lanes(dst, dimp, 8);
+    if (f.kind == FIELD_MERSENNE61)
+        chacha_mask_combine_kernel<true, DRAW_M61><<<grid, CTA, 0, lc.stream>>>(keys, P, sps, dim, dst, dimp, f, dr,
+                                                                                lanes, flag);
+    else
+        chacha_mask_combine_kernel<false, DRAW_GENERIC><<<grid, CTA, 0, lc.stream>>>(keys, P, sps, dim, dst, dimp, f,
+                                                                                     dr, lanes, flag);
+    ++*lc.nlaunch;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || slices == 1) return e;
+    return launch_combine(lc, f, scratch, dimp, slices, dim, nullptr, out, nullptr, 0);
+}
+
+cudaError_t launch_packed_share(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k,
+                                int t, int n, const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P,
+                                size_t dim, const ChaChaKey *keys, const uint64_t *draws, const uint64_t *d_mat,
+                                int64_t *shares_out, unsigned *flag) {
+    if (dim == 0 || P == 0) return cudaSuccess;
+    if (P > 65535) return cudaErrorInvalidValue;
+    const int lazy = lazy_terms(f.m);
+    if (draws == nullptr) {
+#define SDA_CFG(K, T, N)                                                                                     \
+    if (k == K && t == T && n == N) {                                                                        \
+        *lc.kernel_name = f.kind == FIELD_MERSENNE61 ? "packed_share<" #K "," #T "," #N ">/mersenne61"         \
+                                                     : "packed_share<" #K "," #T "," #N ">/generic";          \
+        return packed_dispatch<K, T, N>(lc, f, dr, rounds, lazy, mtx, secrets, ld, P, dim, keys, shares_out, \
+                                        flag);                                                               \
+    }
+        SDA_CFG(3, 2, 5)   // BASELINE config #3
+        SDA_CFG(5, 4, 9)   // BASELINE config #4
+        SDA_CFG(3, 4, 7)   // BASELINE config #5
+        SDA_CFG(3, 4, 8)   // the reference's own test parameters (full_loop.rs:57-64)
+#undef SDA_CFG
+        return cudaErrorInvalidValue;   // caller must pre-draw for other shapes
+    }
+    *lc.kernel_name = "packed_share<draws from memory>";
+    if (d_mat == nullptr) return cudaErrorInvalidValue;
+    const size_t B = (dim + k - 1) / k;
+    dim3 grid((unsigned)((B + CTA - 1) / CTA), (unsigned)P);
+    const uint64_t *mat_g = d_mat;
+    if (f.kind == FIELD_MERSENNE61)
+        packed_share_mem_kernel<true><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, B, k, t, n, mat_g, draws,
+                                                                   shares_out, f, lazy);
+    else
+        packed_share_mem_kernel<false><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, B, k, t, n, mat_g, draws,
+                                                                    shares_out, f, lazy);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+}  // namespace sda

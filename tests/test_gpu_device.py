@@ -1,0 +1,201 @@
+"""Device-pointer entry points and BASELINE-size properties (`-m gpu`).  torch is only the
+device allocator here; every computation under test is a libsda_b200 kernel."""
+import numpy as np
+import pytest
+
+import util
+from sda_b200 import LinearMaskingScheme as LMS
+from sda_b200 import LinearSecretSharingScheme as LSS
+from sda_b200 import params
+
+pytestmark = pytest.mark.gpu
+
+P61 = params.P61
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    torch.cuda.init()
+    return torch
+
+
+def dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def test_synth_fill_matches_oracle(ctx, oracle, torch_cuda):
+    t = torch_cuda
+    for m in (433, P61, params.P61_GENERIC):
+        for start, count in [(0, 1), (0, 8), (3, 5), (5, 100), (1 << 40, 4097), (7, 1)]:
+            out = t.empty(count, dtype=t.int64, device="cuda")
+            ctx.synth_fill_dev(3, m, start, count, out)
+            ctx.synchronize()
+            assert np.array_equal(host(out), oracle.synth_fill(3, m, start, count)), (m, start, count)
+
+
+@pytest.mark.parametrize("mk", [params.config2, params.config3, params.config4, params.config5,
+                                lambda: LSS.Additive(3, 433), params.reference_test])
+def test_share_generate_dev_multi_participant(ctx, oracle, torch_cuda, mk):
+    """P participants in one launch, strided secrets, one seed each"""
+    t = torch_cuda
+    s = mk()
+    rng = np.random.default_rng(2)
+    for P, dim, ld in [(1, 10, 10), (3, 1001, 1004), (5, 4096, 4096), (2, 12289, 12292)]:
+        n, B = s.output_size(), s.batches(dim)
+        secrets = np.zeros((P, ld), dtype=np.int64)
+        secrets[:, :dim] = rng.integers(0, s.modulus, size=(P, dim), dtype=np.int64)
+        seeds = b"".join(util.seed_bytes(f"dev/{P}/{pi}") for pi in range(P))
+        d_in = dev(t, secrets)
+        d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_dev(s, d_in, ld, P, dim, seeds, d_out)
+        ctx.synchronize()
+        got = host(d_out)
+        for pi in range(P):
+            exp = util.oracle_generate(oracle, s, secrets[pi, :dim], seeds[32 * pi:32 * pi + 32], matrix=True)
+            assert np.array_equal(got[pi], util.canon(oracle, s.modulus, exp)), (P, dim, pi)
+
+
+def test_share_combine_dev_accumulate(ctx, oracle, torch_cuda):
+    """streaming tiles into a running sum == one combine over all rows (clerk.rs:71-72 FIXME)"""
+    t = torch_cuda
+    s = params.config4()
+    rng = np.random.default_rng(4)
+    P, L, ld = 300, 5000, 5004
+    rows = np.zeros((P, ld), dtype=np.int64)
+    rows[:, :L] = rng.integers(0, P61, size=(P, L), dtype=np.int64)
+    exp = oracle.share_combine(P61, rows[:, :L].copy())
+    d_rows = dev(t, rows)
+    acc = t.zeros(L, dtype=t.int64, device="cuda")
+    for p0 in range(0, P, 64):
+        pc = min(64, P - p0)
+        ctx.share_combine_dev(s, d_rows[p0:], ld, pc, L, acc, d_acc_in=acc if p0 else None)
+    ctx.synchronize()
+    assert np.array_equal(host(acc), exp)
+    one = t.empty(L, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(s, d_rows, ld, P, L, one)
+    ctx.synchronize()
+    assert np.array_equal(host(one), exp)
+
+
+def test_share_generate_combine_dev(ctx, oracle, torch_cuda):
+    """fused participant->clerk path == generate then per-clerk combine"""
+    t = torch_cuda
+    for s in (params.config3(), params.config2()):
+        P, dim = 7, 3000
+        n, B = s.output_size(), s.batches(dim)
+        rng = np.random.default_rng(8)
+        secrets = rng.integers(0, P61, size=(P, dim), dtype=np.int64)
+        seeds = b"".join(util.seed_bytes(f"fuse/{pi}") for pi in range(P))
+        out = t.empty((n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_combine_dev(s, dev(t, secrets), dim, P, dim, seeds, out)
+        ctx.synchronize()
+        shares = np.stack([util.canon(oracle, P61, util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32],
+                                                                      matrix=True)) for pi in range(P)])
+        exp = np.stack([oracle.share_combine(P61, np.ascontiguousarray(shares[:, c, :])) for c in range(n)])
+        assert np.array_equal(host(out), exp)
+
+
+def test_mod_reduce_and_unmask_dev(ctx, oracle, torch_cuda):
+    t = torch_cuda
+    rng = np.random.default_rng(6)
+    v = rng.integers(-(1 << 63), (1 << 63) - 1, size=10001, dtype=np.int64)
+    for m in (433, P61, params.P61_GENERIC, (1 << 63) - 1):
+        out = t.empty(len(v), dtype=t.int64, device="cuda")
+        ctx.mod_reduce_dev(m, dev(t, v), len(v), out)
+        ctx.synchronize()
+        assert np.array_equal(host(out), util.canon(oracle, m, v))
+    ms = LMS.Full(P61)
+    a, b = rng.integers(0, P61, size=999, dtype=np.int64), rng.integers(0, P61, size=999, dtype=np.int64)
+    out = t.empty(999, dtype=t.int64, device="cuda")
+    ctx.unmask_dev(ms, dev(t, a), dev(t, b), 999, out)
+    ctx.synchronize()
+    assert np.array_equal(host(out), util.canon(oracle, P61, oracle.unmask(util.to_oracle_masking(oracle, ms), a, b)))
+
+
+# ---- BASELINE sizes: parity on the full vector + size-independent properties -------------------------
+def test_config3_full_size(ctx, oracle, torch_cuda):
+    """packed Shamir k=3/n=5, dim = 10M, p = 2^61-1: bit-exact against the oracle on the whole
+    vector, then share -> clerk-sum -> reconstruct == sum of secrets for 3 participants"""
+    t = torch_cuda
+    s = params.config3()
+    dim, P = 10_000_000, 3
+    n, B = 5, s.batches(dim)
+    d_sec = t.empty((P, dim), dtype=t.int64, device="cuda")
+    for pi in range(P):
+        ctx.synth_fill_dev(3, P61, pi * dim, dim, d_sec[pi])
+    seeds = b"".join(util.seed_bytes(f"cfg3/{pi}") for pi in range(P))
+    d_sh = t.empty((P, n, B), dtype=t.int64, device="cuda")
+    ctx.share_generate_dev(s, d_sec, dim, P, dim, seeds, d_sh)
+    ctx.synchronize()
+    sec0 = oracle.synth_fill(3, P61, 0, dim)
+    assert np.array_equal(host(d_sec[0]), sec0)
+    exp0 = util.oracle_generate(oracle, s, sec0, seeds[:32], matrix=True)
+    assert np.array_equal(host(d_sh[0]), exp0)
+    # clerk sums, then reveal from all 5 clerks
+    d_sum = t.empty((n, B), dtype=t.int64, device="cuda")
+    for c in range(n):
+        ctx.share_combine_dev(s, d_sh[:, c, :], n * B, P, B, d_sum[c])
+    d_rec = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.secret_reconstruct_dev(s, dim, list(range(n)), d_sum, B, n, B, d_rec)
+    d_tot = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(s, d_sec, dim, P, dim, d_tot)
+    ctx.synchronize()
+    assert t.equal(d_rec, d_tot)
+    assert int(d_sh.min()) >= 0 and int(d_sh.max()) < P61
+
+
+def test_config2_full_size(ctx, oracle, torch_cuda):
+    """additive 3-way, dim = 1M, p = 2^61-1, 16 participants: split parity on one participant,
+    then sum of the three clerk sums == sum of secrets"""
+    t = torch_cuda
+    s = params.config2()
+    dim, P, n = 1_000_000, 16, 3
+    d_sec = t.empty((P, dim), dtype=t.int64, device="cuda")
+    ctx.synth_fill_dev(2, P61, 0, P * dim, d_sec)
+    seeds = b"".join(util.seed_bytes(f"cfg2/{pi}") for pi in range(P))
+    d_sh = t.empty((P, n, dim), dtype=t.int64, device="cuda")
+    ctx.share_generate_dev(s, d_sec, dim, P, dim, seeds, d_sh)
+    ctx.synchronize()
+    sec5 = oracle.synth_fill(2, P61, 5 * dim, dim)
+    exp = util.canon(oracle, P61, util.oracle_generate(oracle, s, sec5, seeds[5 * 32:6 * 32]))
+    assert np.array_equal(host(d_sh[5]), exp)
+    d_sum = t.empty((n, dim), dtype=t.int64, device="cuda")
+    for c in range(n):
+        ctx.share_combine_dev(s, d_sh[:, c, :], n * dim, P, dim, d_sum[c])
+    d_rec = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.secret_reconstruct_dev(s, dim, [0, 1, 2], d_sum, dim, n, dim, d_rec)
+    d_tot = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(s, d_sec, dim, P, dim, d_tot)
+    ctx.synchronize()
+    assert t.equal(d_rec, d_tot)
+
+
+def test_config4_clerk_sum_slice(ctx, oracle, torch_cuda):
+    """k=5/n=9 clerk job slice [2048][2M] (config #4 shape, 32.8 GB): checksum-of-checksums --
+    the combine of column sums equals the column sums of row-block combines, and sampled
+    columns match the oracle"""
+    t = torch_cuda
+    s = params.config4()
+    P, L = 2048, 2_000_000
+    d_rows = t.empty((P, L), dtype=t.int64, device="cuda")
+    ctx.synth_fill_dev(4, P61, 0, P * L, d_rows)
+    out = t.empty(L, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(s, d_rows, L, P, L, out)
+    parts = t.empty((4, L), dtype=t.int64, device="cuda")
+    for q in range(4):
+        ctx.share_combine_dev(s, d_rows[q * 512:], L, 512, L, parts[q])
+    out2 = t.empty(L, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(s, parts, L, 4, L, out2)
+    ctx.synchronize()
+    assert t.equal(out, out2)
+    cols = [0, 1, 2, 3, 1023, 1024, 999_999, L - 1]
+    sample = host(d_rows[:, cols])
+    exp = oracle.share_combine(P61, np.ascontiguousarray(sample))
+    assert host(out[cols]).tolist() == exp.tolist()
+    del d_rows
+    t.cuda.empty_cache()
