@@ -535,7 +535,9 @@ void sdao_positive(int64_t m, int64_t *v, size_t n) {
     for (size_t i = 0; i < n; i++) if (v[i] < 0) v[i] += m;
 }
 void sdao_canonical(int64_t m, int64_t *v, size_t n) {
-    for (size_t i = 0; i < n; i++) v[i] = ((v[i] % m) + m) % m;
+    /* receive.rs:13-21: `if v < 0 { v + m }` on the truncated remainder (no (r + m) % m: that
+     * overflows i64 for m > 2^62) */
+    for (size_t i = 0; i < n; i++) { int64_t r = v[i] % m; v[i] = r < 0 ? r + m : r; }
 }
 
 /* ======================================================================================
