@@ -11,7 +11,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) k(uint64_t *out, uint32_t a, uint32_t b, long long *cyc) {
     uint64_t acc[ILP];
     uint32_t x[ILP], y[ILP];
-    for (int i = 0; i < ILP; i++) { acc[i] = threadIdx.x + i; x[i] = a + i * 7 + threadIdx.x; y[i] = b ^ (i * 13); }
+    for (int i = 0; i < ILP; i++) { acc[i] = threadIdx.x + i; x[i] = a + i * 7 + threadIdx.x; y[i] = b ^ (i * 13) ^ (threadIdx.x * 3); }
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < N_ITER; it++) {
