@@ -299,35 +299,37 @@ def run_ours(args):
     value = world * T * dim * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host-buffer C-ABI calls, copies inside the timed region ----------------------------
-    Te = args.e2e_participants
-    h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
-    h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
-    h_rows = ctx.pinned_empty(Te * B).reshape(Te, B)
-    h_out = ctx.pinned_empty(n * B).reshape(n, B)
-    for i in range(Te):
-        h_sec[i][:] = d_sec[i].cpu().numpy()
+    Te = 0 if args.no_e2e else args.e2e_participants
+    e2e_value = None
+    if Te > 0:
+        h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
+        h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
+        h_rows = ctx.pinned_empty(Te * B).reshape(Te, B)
+        h_out = ctx.pinned_empty(n * B).reshape(n, B)
+        for i in range(Te):
+            h_sec[i][:] = d_sec[i].cpu().numpy()
 
-    def e2e_step(i):
-        seeds = seeds_for(1000 + i, rank, Te)
-        for q in range(Te):
-            ctx.share_generate(scheme, h_sec[q], seeds[32 * q:32 * q + 32], out=h_sh[q])
-        for cl in range(n):
-            # the clerk receives its column of every participation (server snapshot transpose)
-            np.copyto(h_rows, h_sh[:, cl, :])
-            ctx.share_combine(scheme, h_rows, out=h_out[cl])
+        def e2e_step(i):
+            seeds = seeds_for(1000 + i, rank, Te)
+            for q in range(Te):
+                ctx.share_generate(scheme, h_sec[q], seeds[32 * q:32 * q + 32], out=h_sh[q])
+            for cl in range(n):
+                # the clerk receives its column of every participation (server snapshot transpose)
+                np.copyto(h_rows, h_sh[:, cl, :])
+                ctx.share_combine(scheme, h_rows, out=h_out[cl])
 
-    e2e_step(-1)
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(1, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * Te * dim * e2e_steps / float(t_e.item())
+        e2e_step(-1)
+        if world > 1:
+            dist.barrier()
+        e2e_steps = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            e2e_step(i)
+        e2e_s = time.perf_counter() - t0
+        t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e_value = world * Te * dim * e2e_steps / float(t_e.item())
     h2d = Te * dim * 8 + n * Te * B * 8
     d2h = Te * n * B * 8 + n * B * 8
 
@@ -396,6 +398,7 @@ def main():
     ap.add_argument("--e2e-participants", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="target CPU seconds per reference step")
     ap.add_argument("--ref-dim", type=int, default=500_000)
     args = ap.parse_args()

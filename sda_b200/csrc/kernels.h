@@ -77,6 +77,10 @@ cudaError_t launch_packed_share(const LaunchCtx &lc, const FieldParams &f, const
                                 int t, int n, const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P,
                                 size_t dim, const ChaChaKey *keys, const uint64_t *draws, const uint64_t *d_mat,
                                 int64_t *shares_out, unsigned *flag);
+// the Mersenne-61 instantiation of the above (packed_m61.cu); shapes of packed_share_has_fast_path
+cudaError_t launch_packed_share_m61(const LaunchCtx &lc, int rounds, int k, int t, int n, const Matrix &mtx,
+                                    const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                                    int64_t *shares_out, unsigned *flag);
 // true when launch_packed_share / launch_additive_split have an in-kernel-rng instantiation
 bool packed_share_has_fast_path(int k, int t, int n);
 bool additive_split_has_fast_path(int n);

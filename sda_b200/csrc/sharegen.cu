@@ -190,61 +190,6 @@ struct MatSplit {            // generic field: canonical entries as two 32-bit w
     uint32_t hi[N * W];
 };
 
-// Mersenne-61 matrix entries, centred and split at bit 31 (host-precomputed):
-//   M == c (mod p), c in (-2^60, 2^60),  c = m0 + m1 2^31,  m0 in [-2^30, 2^30), |m1| <= 2^29,  d1 = 2 m1
-template <int N, int W>
-struct MatM61 {
-    int32_t m0[N * W];
-    int32_t m1[N * W];
-    int32_t d1[N * W];
-};
-
-__device__ __forceinline__ int64_t madw_s(int32_t a, int32_t b, int64_t c) {
-    int64_t d;
-    asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t madw_u(uint32_t a, uint32_t b, uint64_t c) {
-    uint64_t d;
-    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(d) : "r"(a), "r"(b), "l"(c));
-    return d;
-}
-
-// (A + X 2^31) mod p for signed 64-bit A, X with |A| < 2^63, |X| < 2^63, canonical result.
-//   X 2^31 = Xl 2^31 + Xh 2^63 == Xl 2^31 + 4 Xh;   A == (A & p) + (A >> 61)   (2^61 == 1)
-__device__ __forceinline__ uint64_t fold_m61(int64_t A, int64_t X) {
-    const uint32_t Xl = (uint32_t)X;
-    const int32_t Xh = (int32_t)(X >> 32);
-    uint64_t t = (uint64_t)madw_s(Xh, 4, (int64_t)P61);       // 4 Xh + p  in (0, 2^62)
-    t = madw_u(Xl, 0x80000000u, t);                           // + Xl 2^31 : < 2^63 + 2^62
-    const uint64_t v = t + ((uint64_t)A & P61) + (uint64_t)(A >> 61);   // in [0, 2^64)
-    uint64_t r = (v & P61) + (v >> 61);                       // <= p + 7
-    return r >= P61 ? r - P61 : r;
-}
-
-// Mersenne-61 dot product of W terms: x = x0 + x1 2^31 (x0 < 2^31, x1 <= 2^30), signed 32x32->64
-// multiply-adds into two accumulators (2^62 == 2 folds the high product into the low one):
-//   A = sum m0 x0 + d1 x1   (|.| < 1.5 2^61 per term),   X = sum m0 x1 + m1 x0   (|.| <= 2^61 per term)
-// 5 terms keep |A| < 2^63; longer rows fold and carry the residue (< 2^61) into chunks of 4 more terms.
-template <int N, int W>
-__device__ __forceinline__ uint64_t dot_m61(const MatM61<N, W> &m, int j, const int32_t (&x0)[W],
-                                            const int32_t (&x1)[W]) {
-    int64_t A = 0, X = 0;
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        if (i >= 5 && (i - 5) % 4 == 0) {    // chunk boundary: carry the residue (< 2^61) in A
-            A = (int64_t)fold_m61(A, X);
-            X = 0;
-        }
-        const int32_t m0 = m.m0[j * W + i], m1 = m.m1[j * W + i], d1 = m.d1[j * W + i];
-        A = madw_s(m0, x0[i], A);
-        A = madw_s(d1, x1[i], A);
-        X = madw_s(m0, x1[i], X);
-        X = madw_s(m1, x0[i], X);
-    }
-    return fold_m61(A, X);
-}
-
 // generic field: 128-bit accumulation, folded every `lazy` terms (lazy * (m-1)^2 + m < m 2^64)
 template <int N, int W>
 __device__ __forceinline__ uint64_t dot_generic(const FieldParams &f, int lazy, const MatSplit<N, W> &m, int j,
@@ -266,16 +211,11 @@ __device__ __forceinline__ uint64_t dot_generic(const FieldParams &f, int lazy, 
     return reduce128_generic(f, hi, lo);
 }
 
-template <bool M61, int N, int W>
-struct MatSel { typedef MatSplit<N, W> type; };
-template <int N, int W>
-struct MatSel<true, N, W> { typedef MatM61<N, W> type; };
-
 template <int K, int T, int N, bool M61, uint32_t DK, int ROUNDS>
 __global__ void __launch_bounds__(CTA)
 packed_share_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B,
                     const ChaChaKey *__restrict__ keys, int64_t *__restrict__ out, FieldParams f, DrawParams dr,
-                    int lazy, typename MatSel<M61, N, K + T>::type mat, int in_lanes, int out_lanes,
+                    int lazy, MatSplit<N, K + T> mat, int in_lanes, int out_lanes,
                     unsigned *flag) {
     constexpr int W = K + T;
     constexpr int G = Unit<T>::G, NB = Unit<T>::NB;
@@ -308,19 +248,8 @@ packed_share_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, 
             x[K + i] = draw_reduce<DK>(dr, blk[q % 8], r);   // tss share(): Range::new(0, prime - 1)
             rej |= r && g < nb;
         }
-        if constexpr (M61) {
-            int32_t x0[W], x1[W];
 #pragma unroll
-            for (int i = 0; i < W; i++) {
-                x0[i] = (int32_t)((uint32_t)x[i] & 0x7fffffffu);
-                x1[i] = (int32_t)(uint32_t)(x[i] >> 31);
-            }
-#pragma unroll
-            for (int j = 0; j < N; j++) sh[j][g] = (int64_t)dot_m61<N, W>(mat, j, x0, x1);
-        } else {
-#pragma unroll
-            for (int j = 0; j < N; j++) sh[j][g] = (int64_t)dot_generic<N, W>(f, lazy, mat, j, x);
-        }
+        for (int j = 0; j < N; j++) sh[j][g] = (int64_t)dot_generic<N, W>(f, lazy, mat, j, x);
     }
     int64_t *o = out + (p * N) * B + b0;
 #pragma unroll
@@ -378,24 +307,6 @@ MatSplit<N, W> split_matrix(const Matrix &m) {
     return s;
 }
 
-template <int N, int W>
-MatM61<N, W> centre_matrix(const Matrix &m) {
-    MatM61<N, W> s;
-    for (int i = 0; i < N * W; i++) {
-        const int64_t c = m.e[i] > P61 / 2 ? (int64_t)m.e[i] - (int64_t)P61 : (int64_t)m.e[i];   // (-2^60, 2^60)
-        const int64_t m1 = (c + (1ll << 30)) >> 31;                                              // round to nearest
-        s.m0[i] = (int32_t)(c - m1 * (1ll << 31));                                               // [-2^30, 2^30)
-        s.m1[i] = (int32_t)m1;
-        s.d1[i] = (int32_t)(2 * m1);
-    }
-    return s;
-}
-template <bool M61, int N, int W>
-typename MatSel<M61, N, W>::type make_kernel_matrix(const Matrix &m) {
-    if constexpr (M61) return centre_matrix<N, W>(m);
-    else return split_matrix<N, W>(m);
-}
-
 template <int K, int T, int N, bool M61, uint32_t DK, int ROUNDS>
 cudaError_t packed_launch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int lazy,
                           const Matrix &mtx, const int64_t *secrets, size_t ld, size_t P, size_t dim,
@@ -407,7 +318,7 @@ cudaError_t packed_launch(const LaunchCtx &lc, const FieldParams &f, const DrawP
     const int in_lanes = pick_lanes(secrets, ld, G * K);
     const int out_lanes = pick_lanes(out, B, G);
     packed_share_kernel<K, T, N, M61, DK, ROUNDS><<<grid, CTA, 0, lc.stream>>>(
-        secrets, ld, dim, B, keys, out, f, dr, lazy, make_kernel_matrix<M61, N, K + T>(mtx), in_lanes, out_lanes, flag);
+        secrets, ld, dim, B, keys, out, f, dr, lazy, split_matrix<N, K + T>(mtx), in_lanes, out_lanes, flag);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
@@ -418,11 +329,6 @@ cudaError_t packed_dispatch(const LaunchCtx &lc, const FieldParams &f, const Dra
                             const ChaChaKey *keys, int64_t *out, unsigned *flag) {
 #define SDA_PL(M61, DK, R) \
     return packed_launch<K, T, N, M61, DK, R>(lc, f, dr, lazy, mtx, secrets, ld, P, dim, keys, out, flag)
-    if (f.kind == FIELD_MERSENNE61) {
-        if (rounds == 8) SDA_PL(true, DRAW_M61_MINUS1, 8);
-        if (rounds == 12) SDA_PL(true, DRAW_M61_MINUS1, 12);
-        SDA_PL(true, DRAW_M61_MINUS1, 20);
-    }
     if (rounds == 8) SDA_PL(false, DRAW_GENERIC, 8);
     if (rounds == 12) SDA_PL(false, DRAW_GENERIC, 12);
     SDA_PL(false, DRAW_GENERIC, 20);
@@ -580,11 +486,13 @@ cudaError_t launch_packed_share(const LaunchCtx &lc, const FieldParams &f, const
     if (dim == 0 || P == 0) return cudaSuccess;
     if (P > 65535) return cudaErrorInvalidValue;
     const int lazy = lazy_terms(f.m);
+    if (draws == nullptr && f.kind == FIELD_MERSENNE61 && packed_share_has_fast_path(k, t, n)) {
+        return launch_packed_share_m61(lc, rounds, k, t, n, mtx, secrets, ld, P, dim, keys, shares_out, flag);
+    }
     if (draws == nullptr) {
 #define SDA_CFG(K, T, N)                                                                                     \
     if (k == K && t == T && n == N) {                                                                        \
-        *lc.kernel_name = f.kind == FIELD_MERSENNE61 ? "packed_share<" #K "," #T "," #N ">/mersenne61"         \
-                                                     : "packed_share<" #K "," #T "," #N ">/generic";          \
+        *lc.kernel_name = "packed_share<" #K "," #T "," #N ">/generic";                                      \
         return packed_dispatch<K, T, N>(lc, f, dr, rounds, lazy, mtx, secrets, ld, P, dim, keys, shares_out, \
                                         flag);                                                               \
     }
