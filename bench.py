@@ -218,6 +218,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = sda_b200.Context(local, rng_rounds=args.rounds)
+    ctx.set_packed_path({"auto": 0, "cuda": 1, "tc": 2}[args.packed_path])
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     scheme = params.config3()
@@ -395,6 +396,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--participants", type=int, default=256, help="resident participants per GPU per step")
     ap.add_argument("--rounds", type=int, default=20, choices=[8, 12, 20], help="ChaCha rounds of the sharing randomness")
+    ap.add_argument("--packed-path", default="auto", choices=["auto", "cuda", "tc"],
+                    help="share-gen kernel: tcgen05 byte-limb GEMM (auto/tc) or the IMAD.WIDE CUDA-core kernel")
     ap.add_argument("--e2e-participants", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

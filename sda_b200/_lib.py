@@ -7,11 +7,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsda_b200.so")
+# SDA_B200_LIB: developer override to A/B another build of the same library
+LIB_PATH = os.environ.get("SDA_B200_LIB") or os.path.join(_HERE, "libsda_b200.so")
 
 SDA_OK, SDA_ERR_INVALID, SDA_ERR_CUDA, SDA_ERR_NCCL, SDA_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SHARING_ADDITIVE, SHARING_PACKED_SHAMIR = 0, 1
 MASK_NONE, MASK_FULL, MASK_CHACHA = 0, 1, 2
+PACKED_PATH_AUTO, PACKED_PATH_CUDA_CORES, PACKED_PATH_TENSOR_CORES = 0, 1, 2
 
 
 class sda_sharing_scheme(C.Structure):
@@ -37,6 +39,7 @@ PROTOTYPES = {
     "sda_last_error": (C.c_char_p, [_vp]),
     "sda_ctx_set_rng_rounds": (_int, [_vp, _int]),
     "sda_ctx_get_rng_rounds": (_int, [_vp]),
+    "sda_ctx_set_packed_path": (_int, [_vp, _int]),
     "sda_ctx_set_stream": (_int, [_vp, _vp]),
     "sda_ctx_get_stream": (_vp, [_vp]),
     "sda_ctx_synchronize": (_int, [_vp]),

@@ -161,6 +161,10 @@ class Context:
     def set_rng_rounds(self, rounds):
         self.check(self._lib.sda_ctx_set_rng_rounds(self._h, rounds))
 
+    def set_packed_path(self, path):
+        """0 auto (tensor cores), 1 CUDA cores, 2 tensor cores: which kernel shares over 2^61-1"""
+        self.check(self._lib.sda_ctx_set_packed_path(self._h, int(path)))
+
     def rng_rounds(self):
         return self._lib.sda_ctx_get_rng_rounds(self._h)
 

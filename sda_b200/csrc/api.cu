@@ -78,7 +78,9 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, mat;
+    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image;
+    int packed_path = SDA_PACKED_PATH_AUTO;
+    std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
     unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
     unsigned *h_flag = nullptr;    // pinned mirror
     PinBuf stage[2];               // pinned staging for pageable host buffers
@@ -420,7 +422,28 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     const ChaChaKey *d_keys = (const ChaChaKey *)ctx->keys.p;
     const bool fast = additive ? (n == 1 || additive_split_has_fast_path(n)) : packed_share_has_fast_path(pk.k, pk.t, pk.n);
     bool exact = !fast;
-    if (fast) {
+    // Mersenne-61 fast shapes: tensor-core kernel unless the context asks for the CUDA-core one
+    const bool use_tc = !additive && fast && f.kind == FIELD_MERSENNE61 && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
+                        packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0;
+    if (use_tc) {
+        const size_t ib = packed_share_tc_image_bytes(pk.k, pk.t, pk.n);
+        std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n};
+        key.insert(key.end(), M.e, M.e + M.rows * M.cols);
+        if (key != ctx->tc_image_key) {
+            std::vector<uint8_t> img(ib);
+            packed_share_tc_build_image(pk.k, pk.t, pk.n, M, img.data());
+            CU(ctx->tc_image.reserve(ib));
+            CU(cudaMemcpyAsync(ctx->tc_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
+            ctx->tc_image_key = key;
+        }
+        OK(clear_flags(ctx));
+        CU(launch_packed_share_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, d_keys,
+                                  (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
+        unsigned rejected = 0;
+        OK(read_flags(ctx, &rejected, nullptr));
+        exact = rejected != 0;
+    } else if (fast) {
         OK(clear_flags(ctx));
         for (size_t p0 = 0; p0 < P; p0 += 65535) {
             const size_t pc = std::min<size_t>(65535, P - p0);
@@ -634,7 +657,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat}) b->release();
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -654,6 +677,13 @@ int sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds) {
     return SDA_OK;
 }
 int sda_ctx_get_rng_rounds(const sda_ctx *ctx) { return ctx ? ctx->rounds : 0; }
+int sda_ctx_set_packed_path(sda_ctx *ctx, int path) {
+    if (!ctx) return SDA_ERR_INVALID;
+    if (path != SDA_PACKED_PATH_AUTO && path != SDA_PACKED_PATH_CUDA_CORES && path != SDA_PACKED_PATH_TENSOR_CORES)
+        return fail(ctx, SDA_ERR_INVALID, "unknown packed-share path %d", path);
+    ctx->packed_path = path;
+    return SDA_OK;
+}
 int sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream) {
     if (!ctx) return SDA_ERR_INVALID;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;

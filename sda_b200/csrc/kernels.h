@@ -81,6 +81,14 @@ cudaError_t launch_packed_share(const LaunchCtx &lc, const FieldParams &f, const
 cudaError_t launch_packed_share_m61(const LaunchCtx &lc, int rounds, int k, int t, int n, const Matrix &mtx,
                                     const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
                                     int64_t *shares_out, unsigned *flag);
+// the tensor-core instantiation (packed_tc.cu): D = bytes(x) . bytes(M 2^8c)^T with tcgen05.mma.kind::i8.
+// The constant operand is built on the host (image_bytes > 0 iff the shape is instantiated) and
+// passed as a 16-byte aligned device copy.
+size_t packed_share_tc_image_bytes(int k, int t, int n);
+void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint8_t *img);
+cudaError_t launch_packed_share_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
+                                   size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
+                                   int64_t *shares_out, unsigned *flag);
 // true when launch_packed_share / launch_additive_split have an in-kernel-rng instantiation
 bool packed_share_has_fast_path(int k, int t, int n);
 bool additive_split_has_fast_path(int n);

@@ -38,6 +38,36 @@ def test_synth_fill_matches_oracle(ctx, oracle, torch_cuda):
             assert np.array_equal(host(out), oracle.synth_fill(3, m, start, count)), (m, start, count)
 
 
+@pytest.mark.parametrize("path", [1, 2], ids=["cuda_cores", "tensor_cores"])
+@pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
+def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
+    """both Mersenne-61 share-gen kernels (IMAD.WIDE limbs / tcgen05 byte-limb GEMM) against the oracle:
+    several participants, dims that end inside a tile, negative and out-of-range secrets"""
+    t = torch_cuda
+    s = mk()
+    k = s.input_size()
+    rng = np.random.default_rng(7)
+    ctx.set_packed_path(path)
+    try:
+        for P, dim in [(1, 1), (2, 128 * k), (3, 512 * k + 1), (2, 3 * 512 * k - 2), (4, 40000)]:
+            n, B = s.output_size(), s.batches(dim)
+            secrets = rng.integers(0, s.modulus, size=(P, dim), dtype=np.int64)
+            secrets[0, ::7] = rng.integers(-(1 << 63), 1 << 63, size=secrets[0, ::7].shape, dtype=np.int64)
+            secrets[-1, ::5] = np.array([0, s.modulus - 1, s.modulus, -1, (1 << 63) - 1, -(1 << 63)] * dim,
+                                        dtype=np.int64)[:secrets[-1, ::5].size]
+            seeds = b"".join(util.seed_bytes(f"paths/{P}/{dim}/{pi}") for pi in range(P))
+            d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+            ctx.share_generate_dev(s, dev(t, secrets), dim, P, dim, seeds, d_out)
+            ctx.synchronize()
+            assert ("tcgen05" in ctx.last_kernel()) == (path == 2)
+            got = host(d_out)
+            for pi in range(P):
+                exp = util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)
+                assert np.array_equal(got[pi], util.canon(oracle, s.modulus, exp)), (path, P, dim, pi)
+    finally:
+        ctx.set_packed_path(0)
+
+
 @pytest.mark.parametrize("mk", [params.config2, params.config3, params.config4, params.config5,
                                 lambda: LSS.Additive(3, 433), params.reference_test])
 def test_share_generate_dev_multi_participant(ctx, oracle, torch_cuda, mk):

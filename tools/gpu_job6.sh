@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+for path in tc cuda; do for r in 20 8; do
+timeout 300 python bench.py --rounds $r --packed-path $path --no-e2e --no-cpu-baseline > gpurun_out/bench_${path}_r$r.json 2> gpurun_out/bench_${path}_r$r.err
+done; done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:packed_share_tc -s 3 -c 1 -o gpurun_out/prof_packed_tc \
+    python bench.py --steps 1 --warmup 3 --participants 16 --no-e2e --no-cpu-baseline > gpurun_out/ncu_packed_tc.log 2>&1
