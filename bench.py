@@ -47,6 +47,7 @@ def workload_config(args, world):
         "dim": DIM, "participants_per_gpu_per_step": args.participants, "participants_total_config": 4096,
         "prime_modulus": (1 << 61) - 1, "omega_secrets": "order 7", "omega_shares": "order 11",
         "rng": f"ChaCha{args.rounds} keystream, rand-0.3 gen_range", "parallelism": f"participants sharded x{world}",
+        "share_gen_kernel": {"auto": "tcgen05 byte-limb GEMM", "tc": "tcgen05 byte-limb GEMM", "cuda": "IMAD.WIDE CUDA cores"}[args.packed_path],
         "l2": "inputs (>= 10 GB per step) far exceed the 126 MB L2; no flush needed",
     }
 
@@ -305,7 +306,6 @@ def run_ours(args):
     if Te > 0:
         h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
         h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
-        h_rows = ctx.pinned_empty(Te * B).reshape(Te, B)
         h_out = ctx.pinned_empty(n * B).reshape(n, B)
         for i in range(Te):
             h_sec[i][:] = d_sec[i].cpu().numpy()
@@ -315,9 +315,9 @@ def run_ours(args):
             for q in range(Te):
                 ctx.share_generate(scheme, h_sec[q], seeds[32 * q:32 * q + 32], out=h_sh[q])
             for cl in range(n):
-                # the clerk receives its column of every participation (server snapshot transpose)
-                np.copyto(h_rows, h_sh[:, cl, :])
-                ctx.share_combine(scheme, h_rows, out=h_out[cl])
+                # the clerk receives its column of every participation (server snapshot transpose,
+                # snapshot.rs:11-27): a `Vec<Vec<Share>>` of P rows, passed as row pointers
+                ctx.share_combine(scheme, [h_sh[q, cl] for q in range(Te)], out=h_out[cl])
 
         e2e_step(-1)
         if world > 1:
@@ -347,8 +347,11 @@ def run_ours(args):
     comb_bytes = n * (T * B * 8 + B * 8)
     comb_avg_ms = sum(comb_ms) / len(comb_ms)
     traffic = load_traffic()
+    traffic_key = "packed_share_bytes_per_launch" if "tcgen05" in kernel_name else "packed_share_cuda_bytes_per_launch"
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic.get("packed_share_bytes_per_launch"),
+                "frac": achieved / peak,
+                "traffic": traffic.get(traffic_key) if (T, args.rounds) == (256, 20) else None,
+                "traffic_source": "profiles/traffic.json (ncu --set full, same launch shape)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": gen_avg_ms,
                 "share_of_step": gen_avg_ms / (gen_avg_ms + comb_avg_ms)}
     kernels = {
@@ -376,10 +379,11 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64 (Z_p, p=2^61-1; 32x32->64 IMAD limbs)", "data": "synthetic",
+        "dtype": "u64 (Z_p, p=2^61-1): u8 byte limbs on tcgen05 kind::i8 with s32 accumulation, 64-bit integer compose"
+                 if "tcgen05" in kernel_name else "u64 (Z_p, p=2^61-1): 32x32->64 IMAD limbs", "data": "synthetic",
         "config": workload_config(args, world), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "participants_per_step": Te, "api": "sda_share_generate + sda_share_combine (pinned host buffers)"},
+                "participants_per_step": Te, "api": "sda_share_generate per participant + sda_share_combine_rows per clerk (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

@@ -1,0 +1,182 @@
+"""Integer models of the two Mersenne-61 share-generation kernels' inner arithmetic.
+
+csrc/packed_m61.cu (centred 31-bit limbs, two 64-bit accumulators, renormalisation every 4 terms,
+offset-cancelling row constant, compare-free fold) and csrc/packed_tc.cu (byte-limb GEMM + compose)
+are exact only because every intermediate stays inside 64 (or 32) bits.  These models restate the
+kernels' word-level operations with Python integers, assert every bound the kernels rely on, and
+compare against plain `sum(c * v) % p` on random and worst-case operands.  No GPU involved.
+"""
+import random
+
+P = (1 << 61) - 1
+M64 = (1 << 64) - 1
+OX1, OA2, OX2 = 1 << 63, -(1 << 60), 6 << 60
+DELTA = (1 << 30) + (1 << 60)
+
+
+def u64(x):
+    assert 0 <= x <= M64, hex(x)
+    return x
+
+
+def s64(x):
+    assert -(1 << 63) <= x < (1 << 63), hex(x)
+    return x
+
+
+def u32(x):
+    assert 0 <= x < (1 << 32), hex(x)
+    return x
+
+
+# ---- packed_m61.cu ------------------------------------------------------------------------------
+def centre_matrix(c):
+    c %= P
+    if c > P // 2:
+        c -= P
+    m1 = (c + (1 << 30)) >> 31
+    m0 = c - (m1 << 31)
+    assert -(1 << 30) <= m0 < (1 << 30) and abs(m1) <= (1 << 29)
+    return m0, m1, 2 * m1
+
+
+def chunks(w):
+    out, i, first = [], 0, True
+    while i < w:
+        n = 5 if first else 4
+        out.append((i, min(w, i + n)))
+        i += n
+        first = False
+    return out
+
+
+def row_const(crow_centred):
+    nb = len(chunks(len(crow_centred))) - 1
+    s = sum(c * DELTA for c in crow_centred) + 1 - nb * OA2 - (OX1 + nb * OX2) * (1 << 31)
+    return (s % P) * pow(2, 30, P) % P
+
+
+def dot_m61(limbs, kp, xs):
+    a, x = 0, OX1 + kp
+    for ci, (lo, hi) in enumerate(chunks(len(xs))):
+        if ci:
+            a = s64((a & P) + (a >> 61) + OA2)
+            x = u64(((x & P) | OX2) + (x >> 61))
+        for i in range(lo, hi):
+            m0, m1, d1 = limbs[i]
+            x0, x1 = xs[i]
+            assert -(1 << 31) <= x0 < (1 << 31) and -(1 << 31) <= x1 < (1 << 31)
+            a = s64(a + m0 * x0 + d1 * x1)
+            x = u64(x + m0 * x1 + m1 * x0)
+    a_lo, a_hi = a & 0xffffffff, (a >> 32) & 0xffffffff
+    t = u64((a_lo | ((a_hi & 0x1fffffff) << 32)) + (x & 0xffffffff) * (1 << 31))
+    t = u64(t + (x >> 32) * 4)
+    t = u64(t + (a >> 61))                       # arithmetic shift: signed top three bits
+    assert t >= 1
+    s = u64(t + (t >> 61))
+    return ((t + (s >> 61) - 1) & M64) & P
+
+
+def limbs_secret(v):
+    assert 0 <= v < (1 << 61)
+    lo, hi = v & 0xffffffff, v >> 32
+    return (lo & 0x7fffffff) - (1 << 30), (((hi << 1) | (lo >> 31)) & 0xffffffff) - (1 << 29)
+
+
+def limbs_draw(v):
+    w0, w1 = v >> 32, v & 0xffffffff
+    l1 = ((w0 << 1) | (w1 >> 31)) & 0x3fffffff
+    return (w1 & 0x7fffffff) + 2 * (w0 >> 29) - (1 << 30), l1 - (1 << 29), l1 == 0x3fffffff
+
+
+EXTREME_C = [1, P - 1, (1 << 60) - 1, 1 << 60, (1 << 60) + 1, P // 2, P // 2 + 1, 1 << 30, (1 << 31) - 1, P - (1 << 30)]
+EXTREME_V = [0, 1, P - 1, P, (1 << 61) - 1, (1 << 31) - 1, 1 << 31, 1 << 60]
+
+
+def run_m61(w, t, trials, extreme, rng):
+    k = w - t
+    for _ in range(trials):
+        crow = [rng.choice(EXTREME_C + [rng.randrange(P)]) if extreme else rng.randrange(P) for _ in range(w)]
+        limbs = [centre_matrix(c) for c in crow]
+        kp = row_const([c if c <= P // 2 else c - P for c in crow])
+        xs, vals = [], []
+        for _ in range(k):
+            v = rng.choice(EXTREME_V) if extreme and rng.random() < .7 else rng.randrange(1 << 61)
+            xs.append(limbs_secret(v))
+            vals.append(v)
+        for _ in range(t):
+            while True:
+                v = rng.choice([0, M64 - 17, (7 << 61) + (1 << 61) - 20, rng.randrange(1 << 64),
+                                (rng.randrange(8) << 61) | ((1 << 61) - 1 - rng.randrange(1 << 31))]) \
+                    if extreme else rng.randrange(1 << 64)
+                x0, x1, unusual = limbs_draw(v)
+                if not unusual:                   # the kernel raises `flag` for these and the host redoes the call
+                    break
+            assert (v & P) + 2 * (v >> 61) == v % (P - 1)
+            xs.append((x0, x1))
+            vals.append(v % (P - 1))
+        assert dot_m61(limbs, kp, xs) == sum(c * v for c, v in zip(crow, vals)) % P
+
+
+def test_packed_m61_inner_arithmetic_is_exact():
+    rng = random.Random(1)
+    for w, t in [(5, 2), (7, 4), (9, 4), (16, 8), (1, 0), (2, 1), (6, 3), (10, 5), (13, 6)]:
+        run_m61(w, t, 3000, False, rng)
+        run_m61(w, t, 3000, True, rng)
+
+
+def test_packed_m61_sign_aligned_worst_case():
+    for w in (5, 9, 16):
+        for crow in ([(1 << 60) - 1] * w, [P - ((1 << 60) - 1)] * w, [(-(1 << 30)) % P] * w):
+            limbs = [centre_matrix(c) for c in crow]
+            kp = row_const([c if c <= P // 2 else c - P for c in crow])
+            for v in (0, (1 << 31) - 1, (1 << 60), (1 << 61) - 1):
+                assert dot_m61(limbs, kp, [limbs_secret(v)] * w) == sum(c * v for c in crow) % P
+
+
+# ---- packed_tc.cu -------------------------------------------------------------------------------
+def compose(d):
+    """limb sums d[s] < 2^23 -> canonical sum_s d[s] 2^{8s} mod p, word for word as the kernel"""
+    assert all(0 <= x < (1 << 23) for x in d)
+    e = [u32(d[2 * i] + (d[2 * i + 1] << 8)) for i in range(4)]
+    lo64, hi64 = e[0] + e[1] * 65536, e[2] + e[3] * 65536
+    l_lo, l_hi, h_lo, h_hi = lo64 & 0xffffffff, lo64 >> 32, hi64 & 0xffffffff, hi64 >> 32
+    small = u32((h_lo >> 29) + h_hi * 8 + 1)
+    t = u64((l_lo | (u32(l_hi + (h_lo & 0x1fffffff)) << 32)) + small)
+    assert 1 <= t < (1 << 62)
+    qm1 = (t >> 61) - 1
+    return ((t + qm1) & M64) & P
+
+
+def tc_share(crow, xs):
+    """one row of the byte-limb GEMM: A = bytes of x, B = bytes of (c 2^{8c'} mod p)"""
+    d = [0] * 8
+    for c, x in zip(crow, xs):
+        assert 0 <= x <= M64
+        for byte in range(8):
+            cst = c * pow(2, 8 * byte, P) % P
+            xb = (x >> (8 * byte)) & 0xff
+            for s in range(8):
+                d[s] += xb * ((cst >> (8 * s)) & 0xff)
+    return compose(d)
+
+
+def test_packed_tc_byte_limb_gemm_is_exact():
+    rng = random.Random(2)
+    for w in (5, 7, 9, 12):                      # 12 values x 8 bytes = 96 bytes of K: the widest tile
+        for trial in range(300):
+            crow = [rng.choice(EXTREME_C + [rng.randrange(P)]) for _ in range(w)]
+            xs = [rng.choice([0, M64, P, P - 1, (1 << 61) + 13, rng.randrange(1 << 64)]) for _ in range(w)]
+            assert tc_share(crow, xs) == sum(c * x for c, x in zip(crow, xs)) % P
+    assert tc_share([P - 1] * 12, [M64] * 12) == (P - 1) * M64 * 12 % P      # every limb sum at its maximum
+
+
+def test_draw_reduction_matches_gen_range_outside_the_flagged_band():
+    rng = random.Random(3)
+    for _ in range(20000):
+        v = rng.choice([rng.randrange(1 << 64), (rng.randrange(8) << 61) | ((1 << 61) - 33 - rng.randrange(1 << 20))])
+        hi, w1 = (v >> 32) & 0x1fffffff, v & 0xffffffff
+        bad = hi == 0x1fffffff and w1 >= 0xffffffe0
+        if not bad:
+            assert v < ((1 << 64) - 16)                                     # accepted by Range::new(0, p - 1)
+            assert (v & P) + 2 * (v >> 61) == v % (P - 1)
