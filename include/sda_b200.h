@@ -94,9 +94,9 @@ const char *sda_last_error(const sda_ctx *ctx);
  * The ChaCha *mask scheme* (chacha.rs) is wire format and always uses 20. */
 int         sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds);
 int         sda_ctx_get_rng_rounds(const sda_ctx *ctx);
-/* Which kernel generates packed-Shamir shares over 2^61-1 for the instantiated shapes: the
- * tcgen05 (tensor-core, byte-limb GEMM) one or the CUDA-core (IMAD.WIDE) one.  Both are exact and
- * produce identical shares; AUTO picks the tensor-core kernel. */
+/* Which kernels evaluate the packed-Shamir maps over 2^61-1 (share generation for the instantiated
+ * shapes, reconstruction for k, m' <= 16): the tcgen05 (tensor-core, byte-limb GEMM) ones or the
+ * CUDA-core ones.  Both are exact and produce identical results; AUTO picks the tensor-core kernels. */
 enum { SDA_PACKED_PATH_AUTO = 0, SDA_PACKED_PATH_CUDA_CORES = 1, SDA_PACKED_PATH_TENSOR_CORES = 2 };
 int         sda_ctx_set_packed_path(sda_ctx *ctx, int path);
 /* stream (cudaStream_t) the *_dev entry points launch on; default: a context-owned stream */

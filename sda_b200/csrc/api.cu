@@ -78,9 +78,10 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image;
+    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image, tc_image_r;
     int packed_path = SDA_PACKED_PATH_AUTO;
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
+    std::vector<uint64_t> tc_image_r_key; // (k, m', R) likewise for the reconstruction operand
     unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
     unsigned *h_flag = nullptr;    // pinned mirror
     PinBuf stage[2];               // pinned staging for pageable host buffers
@@ -513,6 +514,21 @@ int reconstruct_core(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension
     Matrix R;
     OK(reconstruct_matrix(ctx, pk, indices, m, &R));
     const FieldParams f = make_field(pk.p);
+    if (f.kind == FIELD_MERSENNE61 && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES && reveal_tc_supported(pk.k, (int)m)) {
+        const size_t ib = reveal_tc_image_bytes(pk.k, (int)m);
+        std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)m};
+        key.insert(key.end(), R.e, R.e + R.rows * R.cols);
+        if (key != ctx->tc_image_r_key) {           // same clerk subset as the previous call: operand still resident
+            std::vector<uint8_t> img(ib);
+            reveal_tc_build_image(pk.k, (int)m, R, img.data());
+            CU(ctx->tc_image_r.reserve(ib));
+            CU(cudaMemcpyAsync(ctx->tc_image_r.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
+            ctx->tc_image_r_key = key;
+        }
+        CU(launch_reveal_tc(ctx->lc(), pk.k, (int)m, d_shares, ld, dimension, (const uint8_t *)ctx->tc_image_r.p, d_out));
+        return SDA_OK;
+    }
     CU(launch_packed_reconstruct(ctx->lc(), f, pk.k, (int)m, R, d_shares, ld, dimension, d_out));
     return SDA_OK;
 }
@@ -657,7 +673,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     if (!ctx) return;
     DeviceGuard g(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image}) b->release();
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);

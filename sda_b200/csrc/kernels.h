@@ -98,6 +98,14 @@ bool additive_split_has_fast_path(int n);
 cudaError_t launch_packed_reconstruct(const LaunchCtx &lc, const FieldParams &f, int k, int m, const Matrix &R,
                                       const int64_t *shares, size_t ld, size_t dimension, int64_t *secrets_out);
 
+// the same map over 2^61 - 1 on the tensor cores (reveal_tc.cu), any k <= 16, m <= 16; the constant
+// operand is built on the host and passed as a 16-byte aligned device copy
+bool reveal_tc_supported(int k, int m);
+size_t reveal_tc_image_bytes(int k, int m);
+void reveal_tc_build_image(int k, int m, const Matrix &R, uint8_t *img);
+cudaError_t launch_reveal_tc(const LaunchCtx &lc, int k, int m, const int64_t *shares, size_t ld, size_t dimension,
+                             const uint8_t *d_b_image, int64_t *secrets_out);
+
 // ---- synthetic inputs ---------------------------------------------------------------------
 cudaError_t launch_synth_fill(const LaunchCtx &lc, const FieldParams &f, uint32_t stream_id, uint64_t start,
                               size_t count, int64_t *out);

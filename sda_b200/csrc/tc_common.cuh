@@ -1,0 +1,89 @@
+// tc_common.cuh -- device helpers shared by the tcgen05 kernels (packed_tc.cu, reveal_tc.cu): UMMA shared-memory
+// descriptors for the no-swizzle K-major operand layout, the kind::i8 MMA, mbarrier waits, TMEM loads, and
+// the composition of eight byte-limb sums into a canonical residue mod 2^61 - 1.
+//
+// Operand layout (both operands, u8, K-major, SWIZZLE_NONE): a core matrix is 8 rows x 16 bytes stored
+// contiguously (128 bytes); LBO = 128 bytes steps to the next 16-byte chunk along K, SBO steps to the next
+// 8 rows.  Row r, K byte kb of a tile therefore lives at (r / 8) * SBO + (kb / 16) * 128 + (r % 8) * 16 + kb % 16.
+// One MMA consumes 32 bytes of K = two chunks.  tools/tc_probe.cu checks this encoding against a host GEMM.
+#pragma once
+#include <cstdint>
+
+#include "field.cuh"
+
+namespace sda {
+namespace tc {
+
+constexpr uint32_t LBO = 128;
+constexpr uint32_t LOW29 = 0x1fffffffu;
+
+// instruction descriptor: s32 accumulators, u8 x u8, both operands K-major, M = 128, N = n_mma (multiple of 16)
+__host__ __device__ constexpr uint32_t idesc_u8(int n_mma) {
+    return (2u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        :: "r"(taddr), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
+__device__ __forceinline__ void unpack(uint64_t v, uint32_t &lo, uint32_t &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mac_u(uint32_t a, uint32_t b, uint64_t c) {     // see packed_m61.cu
+    uint64_t d;
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %1, %2;\n\tadd.u64 %0, %3, t;\n\t}" : "=l"(d) : "r"(a), "r"(b), "l"(c));
+    return d;
+}
+
+// canonical  sum_s d[s] 2^{8s}  mod p  for limb sums d[s] < 2^23
+__device__ __forceinline__ uint64_t compose(const uint32_t (&d)[8], uint32_t two16) {
+    const uint32_t e0 = d[0] + (d[1] << 8), e1 = d[2] + (d[3] << 8);            // < 2^31.6
+    const uint32_t e2 = d[4] + (d[5] << 8), e3 = d[6] + (d[7] << 8);
+    const uint64_t L = mac_u(e1, two16, e0), H = mac_u(e3, two16, e2);           // < 2^48: value = L + H 2^32
+    uint32_t l_lo, l_hi, h_lo, h_hi;
+    unpack(L, l_lo, l_hi);
+    unpack(H, h_lo, h_hi);
+    // H 2^32 = (h_lo & 2^29-1) 2^32 + (h_lo >> 29) 2^61 + h_hi 2^64 == (..) 2^32 + (h_lo >> 29) + 8 h_hi
+    const uint32_t small = (h_lo >> 29) + (h_hi * 8u + 1u);                     // + 1: t == value + 1
+    const uint64_t t = pack(l_lo, l_hi + (h_lo & LOW29)) + small;               // in [1, 2^62)
+    uint32_t t_lo, t_hi;
+    unpack(t, t_lo, t_hi);
+    const int64_t qm1 = (int64_t)(int32_t)((t_hi >> 29) - 1u);                  // floor((t - 1) / p) - 1 in {-1, 0}
+    uint32_t r_lo, r_hi;
+    unpack(t + (uint64_t)qm1, r_lo, r_hi);
+    return pack(r_lo, r_hi & LOW29);
+}
+
+__device__ __forceinline__ uint64_t canon_negative(int64_t v) {                 // v < 0 -> [0, p)
+    const uint64_t a = 0ull - (uint64_t)v;
+    uint64_t r = (a & P61) + (a >> 61);
+    r = r >= P61 ? r - P61 : r;
+    return r ? P61 - r : 0;
+}
+
+
+}  // namespace tc
+}  // namespace sda

@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Per-kernel measurements of every hot-path row at BASELINE-like sizes on one
+B200: device-resident inputs, CUDA events on the context's stream, best and median of `--reps`
+launches after 3 warm-ups, algorithmic bytes / time against the measured HBM copy peak.
+Developer/evidence tool: `python tools/kernel_bench.py > gpurun_out/kernels.jsonl` (one JSON line each).
+Working sets are several GB per launch (>> 126 MB L2), so there is no cache flush between launches."""
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import sda_b200  # noqa: E402
+from sda_b200 import LinearMaskingScheme as LMS  # noqa: E402
+from sda_b200 import params  # noqa: E402
+
+
+def peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--rounds", type=int, default=20)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    torch.cuda.set_device(0)
+    ctx = sda_b200.Context(0, rng_rounds=args.rounds)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    peak = peak_gbs()
+    P61 = params.P61
+
+    def seeds(tag, n):
+        return b"".join(hashlib.sha256(b"%s/%d" % (tag.encode(), i)).digest() for i in range(n))
+
+    def timeit(name, fn, elements, alg_bytes, note=""):
+        if args.only and args.only not in name:
+            return
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                fn()
+            ctx.synchronize()
+            ts = []
+            for _ in range(args.reps):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                fn()
+                b.record(stream)
+                ctx.synchronize()
+                ts.append(a.elapsed_time(b))
+        best, med = min(ts), statistics.median(ts)
+        line = {"kernel": name, "ms_best": best, "ms_median": med, "elements": elements,
+                "elements_per_s": elements / (med * 1e-3), "algorithmic_bytes": alg_bytes,
+                "GBps": alg_bytes / (med * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (med * 1e-3) / 1e9 / peak,
+                "peak_GBps": peak, "variant": ctx.last_kernel(), "rng_rounds": args.rounds, "note": note}
+        print(json.dumps(line), flush=True)
+
+    def empty(*shape):
+        return torch.empty(shape, dtype=torch.int64, device="cuda")
+
+    with torch.cuda.stream(stream):
+        # ---- config #2: additive n=3, dim=1M, 1024 participants ------------------------------------
+        s2, P, dim = params.config2(), 1024, 1_000_000
+        sec = empty(P, dim)
+        ctx.synth_fill_dev(2, P61, 0, P * dim, sec)
+        sh = empty(P, 3, dim)
+        sd = seeds("c2", P)
+        timeit("additive_split cfg2 [1024][1M] n=3", lambda: ctx.share_generate_dev(s2, sec, dim, P, dim, sd, sh),
+               P * dim, P * dim * 8 * 4, "read 8 + write 24 B per secret")
+        out = empty(dim)
+        timeit("combine cfg2 clerk job [1024][1M] (strided view of the shares)",
+               lambda: ctx.share_combine_dev(s2, sh[:, 0, :], 3 * dim, P, dim, out), P * dim, P * dim * 8 + dim * 8)
+        timeit("additive_reconstruct 3 x [1M]", lambda: ctx.share_combine_dev(s2, sh[0], dim, 3, dim, out), dim,
+               4 * dim * 8, "launch-bound at this size")
+        del sec, sh, out
+        torch.cuda.empty_cache()
+
+        # ---- configs #4 / #5: packed share generation -------------------------------------------------
+        for name, mk, P in (("cfg3 k=3 n=5 t=2", params.config3, 128), ("cfg4 k=5 n=9 t=4", params.config4, 128),
+                            ("cfg5 k=3 n=7 t=4", params.config5, 128)):
+            s, dim = mk(), 10_000_000
+            n, B = s.output_size(), s.batches(dim)
+            sec = empty(P, dim)
+            ctx.synth_fill_dev(4, P61, 0, P * dim, sec)
+            sh = empty(P, n, B)
+            sd = seeds(name, P)
+            for path, label in ((2, "tensor cores"), (1, "CUDA cores")):
+                ctx.set_packed_path(path)
+                timeit(f"packed_share {name} [{P}][10M] ({label})",
+                       lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n * B) * 8,
+                       f"8(1+n/k) = {8 * (1 + n / s.input_size()):.2f} B per secret")
+            ctx.set_packed_path(0)
+            if "cfg4" in name:
+                out = empty(B)
+                timeit("combine cfg4 clerk job [128][2M] (strided view)",
+                       lambda: ctx.share_combine_dev(s, sh[:, 0, :], n * B, P, B, out), P * B, P * B * 8 + B * 8)
+                rec = empty(dim)
+                timeit("packed_reconstruct cfg4 9 x [2M] -> [10M]",
+                       lambda: ctx.secret_reconstruct_dev(s, dim, list(range(n)), sh[0], B, n, B, rec), dim,
+                       (n * B + dim) * 8, "read 8 m' + write 8 k B per batch")
+                del out, rec
+            del sec, sh
+            torch.cuda.empty_cache()
+
+        # ---- reveal with a missing clerk: the reference's own test shape over the 61-bit prime --------------
+        s = params.LinearSecretSharingScheme.PackedShamir(3, 8, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
+        dim = 10_000_000
+        B = s.batches(dim)
+        rows = empty(7, B)
+        ctx.synth_fill_dev(7, P61, 0, 7 * B, rows)
+        rec = empty(dim)
+        timeit("packed_reconstruct k=3 t=4 n=8, clerks {0..5,7} x [3.33M] -> [10M]",
+               lambda: ctx.secret_reconstruct_dev(s, dim, [0, 1, 2, 3, 4, 5, 7], rows, B, 7, B, rec), dim, (7 * B + dim) * 8)
+        del rows, rec
+        torch.cuda.empty_cache()
+
+        # ---- masks, dim = 25M (config #5's vector) --------------------------------------------------------
+        dim = 25_000_000
+        sec = empty(dim)
+        ctx.synth_fill_dev(5, P61, 0, dim, sec)
+        mask, masked, back = empty(dim), empty(dim), empty(dim)
+        full, cc = LMS.Full(P61), LMS.ChaCha(P61, dim, 128)
+        seed = hashlib.sha256(b"mask").digest()
+        timeit("full_mask [25M]", lambda: ctx.mask_dev(full, sec, dim, seed, mask, masked), dim, dim * 8 * 3,
+               "read 8 + write mask 8 + masked 8")
+        timeit("chacha_mask [25M] (20 rounds, wire format)", lambda: ctx.mask_dev(cc, sec, dim, seed, mask, masked), dim,
+               dim * 8 * 2, "read 8 + write masked 8; the mask is the 4 seed words")
+        timeit("unmask [25M]", lambda: ctx.unmask_dev(full, mask, masked, dim, back), dim, dim * 8 * 3)
+        Pm = 256
+        seeds_t = torch.randint(0, 1 << 32, (Pm, 4), dtype=torch.int64, device="cuda")
+        timeit(f"chacha_mask_combine {Pm} seeds x [25M]", lambda: ctx.mask_combine_dev(cc, seeds_t, Pm, 4, back), Pm * dim,
+               dim * 8, "compute-bound by construction: P keystream blocks per 8 outputs, elements = draws")
+        masks = empty(64, dim)
+        ctx.synth_fill_dev(6, P61, 0, 64 * dim, masks)
+        timeit("full_mask_combine [64][25M]", lambda: ctx.mask_combine_dev(full, masks, 64, dim, back), 64 * dim,
+               65 * dim * 8)
+
+
+if __name__ == "__main__":
+    main()
