@@ -40,6 +40,18 @@ namespace {
 
 using namespace tc;
 
+#ifndef SDA_TC_PREFETCH
+#define SDA_TC_PREFETCH 2   // where the next pass's secrets are loaded: 1 under the last tile's compose, 2 before the tile loop
+#endif
+
+#ifndef SDA_TC_MINBLOCKS
+#define SDA_TC_MINBLOCKS 1
+#endif
+#ifndef SDA_TC_UNROLL
+#define SDA_TC_UNROLL 2
+#endif
+
+constexpr int kChaChaUnroll = SDA_TC_UNROLL;   // double rounds per iteration of the (otherwise rolled) keystream loop
 constexpr int CTA = 128;             // threads = rows of one MMA tile = TMEM lanes
 
 constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
@@ -49,19 +61,24 @@ struct Shape {
     static_assert(T % 2 == 0 && T >= 2, "draws fill whole 16-byte chunks");
     static constexpr int G = 8 / gcd_c(T, 8);              // 128-batch tiles per pass of a CTA
     static constexpr int NB = T / gcd_c(T, 8);             // keystream blocks per thread per pass
+    // A row = [draws | secrets]; the two parts live in separate buffers (the draws double-buffered, so the
+    // keystream of the next pass is computed under this pass's MMAs) and are consumed by separate K steps
     static constexpr int DC = T / 2;                       // 16-byte chunks of a row holding draws
     static constexpr int SC = (K + 1) / 2;                 // ... holding secrets
-    static constexpr int C = DC + SC;
-    static constexpr int NK = (C + 1) / 2;                 // MMAs per tile (32 bytes of K each)
-    static constexpr uint32_t SBO_A = C * 128;             // an odd last chunk aliases the next group: B is 0 there
-    static constexpr uint32_t A_TILE = 16 * SBO_A;
-    static constexpr uint32_t A_BYTES = G * A_TILE + 128;  // + the aliased chunk past the last group
+    static constexpr int NKD = (DC + 1) / 2, NKS = (SC + 1) / 2;
+    static constexpr int NK = NKD + NKS;                   // MMAs per tile (32 bytes of K each)
+    // an odd chunk count lets the second chunk of the last K step alias the next 8-row group: B is 0 there
+    static constexpr uint32_t SBO_D = DC * 128, SBO_S = SC * 128;
+    static constexpr uint32_t D_TILE = 16 * SBO_D, S_TILE = 16 * SBO_S;
+    static constexpr uint32_t D_BYTES = G * D_TILE + 128, S_BYTES = G * S_TILE + 128;
     static constexpr int NMMA = (8 * N + 15) / 16 * 16;
     static constexpr uint32_t SBO_B = 2 * NK * 128;
     static constexpr uint32_t B_BYTES = NMMA / 8 * SBO_B;
+    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + B_BYTES;
     static constexpr int TMEM_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : NMMA <= 128 ? 128 : 256;
     static constexpr uint32_t IDESC = idesc_u8(NMMA);
     static_assert(4 % DC == 0, "a keystream block covers whole rows");
+    static_assert(D_BYTES % 128 == 0 && S_BYTES % 128 == 0, "operand buffers stay 128-byte aligned");
 };
 
 #define SDA_QR(a, b, c, d)                                      \
@@ -78,7 +95,7 @@ __device__ __forceinline__ void chacha_block(const uint32_t (&k)[8], uint64_t bl
     uint32_t x4 = k[0], x5 = k[1], x6 = k[2], x7 = k[3];
     uint32_t x8 = k[4], x9 = k[5], x10 = k[6], x11 = k[7];
     uint32_t x12 = b0, x13 = b1, x14 = 0, x15 = 0;
-#pragma unroll 2
+#pragma unroll kChaChaUnroll
     for (int i = 0; i < ROUNDS / 2; i++) {
         SDA_QR(x0, x4, x8, x12)
         SDA_QR(x1, x5, x9, x13)
@@ -95,38 +112,106 @@ __device__ __forceinline__ void chacha_block(const uint32_t (&k)[8], uint64_t bl
     o[12] = x12 + b0;   o[13] = x13 + b1;   o[14] = x14;         o[15] = x15;
 }
 
-// draw (hi word w0, lo word w1) -> v mod (p - 1) as (v & p) + 2 (v >> 61); `bad` when that is not gen_range's answer
-__device__ __forceinline__ uint64_t reduce_draw(uint32_t w0, uint32_t w1, bool &bad) {
+// draw (hi word w0, lo word w1) -> v mod (p - 1) as (v & p) + 2 (v >> 61).  That is gen_range's answer
+// unless v mod 2^61 >= 2^61 - 32 (a rejected word or a wrap-around).  The necessary condition "bits 32..60
+// all ones" (2^-29 per draw) is accumulated arithmetically -- hi + 1 carries into bit 29 exactly then -- so
+// it costs half an ALU instruction per draw, and the caller settles the rare case exactly.
+__device__ __forceinline__ uint64_t reduce_draw(uint32_t w0, uint32_t w1, uint32_t &suspect) {
     const uint32_t h = w0 >> 29, hi = w0 & LOW29;
-    bad = hi == LOW29 && w1 >= 0xffffffe0u;          // v mod 2^61 >= 2^61 - 32: rejected word or wrap-around
+    suspect |= hi + 1u;
     return pack(w1, hi) + (uint64_t)(2u * h);
 }
 
 // one thread: the NK MMAs of a 128-row tile, completion signalled on `full_bar`
 template <class S>
-__device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t a_tile, uint32_t b_base, uint32_t full_bar) {
-    const uint64_t da = umma_desc(a_tile, S::SBO_A), db = umma_desc(b_base, S::SBO_B);
+__device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_base, uint32_t full_bar) {
+    const uint64_t dd = umma_desc(d_tile, S::SBO_D), ds = umma_desc(s_tile, S::SBO_S), db = umma_desc(b_base, S::SBO_B);
 #pragma unroll
-    for (int kk = 0; kk < S::NK; kk++)
-        umma_i8(taddr, da + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S::IDESC, kk > 0);
+    for (int kk = 0; kk < S::NKD; kk++)
+        umma_i8(taddr, dd + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S::IDESC, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < S::NKS; kk++)
+        umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
 }
 
+// the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to
+template <class S, int ROUNDS>
+__device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, size_t p, size_t u, int tid, uint8_t *sD,
+                                            unsigned *flag) {
+    uint32_t k[8];
+    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
+    const uint4 ka = __ldg(src), kb = __ldg(src + 1);
+    k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
+    k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
+#pragma unroll 1
+    for (int nb = 0; nb < S::NB; nb++) {
+        const uint32_t slot = nb * CTA + tid;                     // block of this pass, in stream order
+        uint32_t w[16];
+        chacha_block<ROUNDS>(k, u * (size_t)(CTA * S::NB) + slot, w);
+        uint32_t suspect = 0;
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) {                          // 4 chunks of 2 draws
+            const uint64_t xa = reduce_draw(w[4 * cb], w[4 * cb + 1], suspect);
+            const uint64_t xb = reduce_draw(w[4 * cb + 2], w[4 * cb + 3], suspect);
+            const uint32_t gc = slot * 4 + cb;                    // chunk index of the pass
+            const uint32_t batch = gc / S::DC, c = gc % S::DC;
+            const uint32_t q = batch / CTA, row = batch % CTA;
+            uint32_t xal, xah, xbl, xbh;
+            unpack(xa, xal, xah);
+            unpack(xb, xbl, xbh);
+            *reinterpret_cast<uint4 *>(sD + q * S::D_TILE + (row >> 3) * S::SBO_D + c * LBO + (row & 7) * 16) =
+                make_uint4(xal, xah, xbl, xbh);
+        }
+        if (suspect & (1u << 29)) {
+            bool bad = false;
+#pragma unroll
+            for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;
+            if (bad) atomicOr(flag, 1u);
+        }
+    }
+}
+
+// the K secrets of row `tid` of each of the G tiles of pass (p, u) into registers; the last batch of a
+// vector is zero padded (batched.rs:38-43)
+template <class S, int K>
+__device__ __forceinline__ void load_secrets(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t p, size_t u,
+                                             int tid, int64_t (&s)[S::G][2 * S::SC]) {
+    const int64_t *sec = secrets + p * ld;
+    const size_t b0 = u * (size_t)(S::G * CTA);
+    const size_t e_first = (b0 + tid) * K;
+    if ((b0 + (size_t)S::G * CTA) * K <= dim) {                                       // whole pass inside the vector
+        const int64_t *src = sec + e_first;
+#pragma unroll
+        for (int q = 0; q < S::G; q++)
+#pragma unroll
+            for (int i = 0; i < 2 * S::SC; i++) s[q][i] = i < K ? __ldg(src + q * (CTA * K) + i) : 0;
+    } else {
+#pragma unroll
+        for (int q = 0; q < S::G; q++) {
+            const size_t e0 = e_first + (size_t)q * (CTA * K);
+#pragma unroll
+            for (int i = 0; i < 2 * S::SC; i++) s[q][i] = (i < K && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+        }
+    }
+}
+
 template <int K, int T, int N, int ROUNDS>
-__global__ void __launch_bounds__(CTA)
+__global__ void __launch_bounds__(CTA, SDA_TC_MINBLOCKS)
 packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t units_per_p,
                        size_t units_total, const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
                        int64_t *__restrict__ out, uint32_t two16, unsigned *flag) {
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *sA = smem;                                   // G tiles of 128 rows
-    uint8_t *sB = smem + ((S::A_BYTES + 127) & ~127u);    // the constant operand
+    uint8_t *sD = smem;                                    // 2 x (G tiles x 128 rows x draws)
+    uint8_t *sS = smem + 2 * S::D_BYTES;                   // G tiles x 128 rows x secrets
+    uint8_t *sB = sS + S::S_BYTES;                         // the constant operand
     __shared__ __align__(8) uint64_t mbar[2];              // [0] full (MMA done), [1] drained (TMEM read out)
     __shared__ uint32_t tmem_base;
 
     const int tid = threadIdx.x, warp = tid >> 5;
 
-    // ---- one-time setup: TMEM, barrier, constant operand ------------------------------------
+    // ---- one-time setup: TMEM, barriers, constant operand ------------------------------------
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      :: "r"(smem_u32(&tmem_base)), "n"(S::TMEM_COLS) : "memory");
@@ -145,88 +230,67 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     const uint32_t taddr = tmem_base;
     const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
     const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[1]);
-    const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-    uint32_t parity = 0;
+    const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
+    const size_t row_bytes = B * sizeof(int64_t);           // distance between the share rows of a participant
+    uint32_t parity = 0, buf = 0;
 
-    size_t p = blockIdx.x / units_per_p, u = blockIdx.x % units_per_p;   // (participant, pass) of this CTA's unit
-    for (size_t unit = blockIdx.x; unit < units_total; unit += gridDim.x, u += gridDim.x) {
-        while (u >= units_per_p) {
-            u -= units_per_p;
-            p++;
-        }
+    // (participant, pass) of this CTA's current unit and of its next one
+    size_t p = blockIdx.x / units_per_p, u = blockIdx.x % units_per_p;
+    int64_t s[S::G][2 * S::SC];                              // secrets of the coming pass, prefetched
+    if (blockIdx.x < units_total) {
+        load_secrets<S, K>(secrets, ld, dim, p, u, tid, s);
+        stage_draws<S, ROUNDS>(keys, p, u, tid, sD, flag);
+    }
+
+    for (size_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
         const size_t b_base_batch = u * (size_t)(S::G * CTA);
-        const int64_t *sec = secrets + p * ld;
-
-        // ---- secrets of row `tid` of every tile: loads issued now, consumed after the keystream ----
-        int64_t s[S::G][2 * S::SC];
-#pragma unroll
-        for (int q = 0; q < S::G; q++) {
-            const size_t e0 = (b_base_batch + (size_t)q * CTA + tid) * K;
-#pragma unroll
-            for (int i = 0; i < 2 * S::SC; i++)
-                s[q][i] = (i < K && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;           // batched.rs:38-43 zero padding
-        }
-        // ---- randomness: NB keystream blocks per thread, reduced and scattered into the rows --
+        // ---- secrets of row `tid` of every tile (loaded during the previous pass): their little-endian
+        //      bytes are the limbs ----------------------------------------------------------------------
         {
-            uint32_t k[8];
-            const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
-            const uint4 ka = __ldg(src), kb = __ldg(src + 1);
-            k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
-            k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
-            bool any_bad = false;
-#pragma unroll 1
-            for (int nb = 0; nb < S::NB; nb++) {
-                const uint32_t slot = nb * CTA + tid;                     // block of this pass, in stream order
-                uint32_t w[16];
-                chacha_block<ROUNDS>(k, u * (size_t)(CTA * S::NB) + slot, w);
 #pragma unroll
-                for (int cb = 0; cb < 4; cb++) {                          // 4 chunks of 2 draws
-                    bool bad0, bad1;
-                    const uint64_t xa = reduce_draw(w[4 * cb], w[4 * cb + 1], bad0);
-                    const uint64_t xb = reduce_draw(w[4 * cb + 2], w[4 * cb + 3], bad1);
-                    any_bad |= bad0 | bad1;
-                    const uint32_t gc = slot * 4 + cb;                    // chunk index of the pass
-                    const uint32_t batch = gc / S::DC, c = gc % S::DC;
-                    const uint32_t q = batch / CTA, row = batch % CTA;
-                    uint32_t xal, xah, xbl, xbh;
-                    unpack(xa, xal, xah);
-                    unpack(xb, xbl, xbh);
-                    *reinterpret_cast<uint4 *>(sA + q * S::A_TILE + (row >> 3) * S::SBO_A + c * LBO + (row & 7) * 16) =
-                        make_uint4(xal, xah, xbl, xbh);
+            for (int q = 0; q < S::G; q++) {
+                uint32_t sign = 0;
+#pragma unroll
+                for (int i = 0; i < K; i++) sign |= (uint32_t)((uint64_t)s[q][i] >> 32);
+                if ((int32_t)sign < 0) {
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                        if (s[q][i] < 0) s[q][i] = (int64_t)canon_negative(s[q][i]);
+                }
+#pragma unroll
+                for (int c = 0; c < S::SC; c++) {
+                    uint32_t al, ah, bl, bh;
+                    unpack((uint64_t)s[q][2 * c], al, ah);
+                    unpack((uint64_t)s[q][2 * c + 1], bl, bh);
+                    *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) =
+                        make_uint4(al, ah, bl, bh);
                 }
             }
-            if (any_bad) atomicOr(flag, 1u);
         }
-        // ---- secrets into the rows: their little-endian bytes are the limbs ----------------------
-#pragma unroll
-        for (int q = 0; q < S::G; q++) {
-            uint32_t sign = 0;
-#pragma unroll
-            for (int i = 0; i < K; i++) sign |= (uint32_t)((uint64_t)s[q][i] >> 32);
-            if ((int32_t)sign < 0) {
-#pragma unroll
-                for (int i = 0; i < K; i++)
-                    if (s[q][i] < 0) s[q][i] = (int64_t)canon_negative(s[q][i]);
-            }
-#pragma unroll
-            for (int c = 0; c < S::SC; c++) {
-                uint32_t al, ah, bl, bh;
-                unpack((uint64_t)s[q][2 * c], al, ah);
-                unpack((uint64_t)s[q][2 * c + 1], bl, bh);
-                *reinterpret_cast<uint4 *>(sA + q * S::A_TILE + (tid >> 3) * S::SBO_A + (S::DC + c) * LBO + (tid & 7) * 16) =
-                    make_uint4(al, ah, bl, bh);
-            }
-        }
+        // rows complete: the secrets just written and the draws written during the previous pass
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_cur = d_base + buf * S::D_BYTES;
+        if (tid == 0) issue_tile<S>(taddr, d_cur, s_base, b_base, full_bar);
+
+        // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
+        size_t pn = p, un = u + gridDim.x;
+        while (un >= units_per_p) {
+            un -= units_per_p;
+            pn++;
+        }
+        const bool more = unit + gridDim.x < units_total;
+        if (more) stage_draws<S, ROUNDS>(keys, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
+#if SDA_TC_PREFETCH == 2
+        if (more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
+#endif
 
         // ---- per tile: D = A . B^T on the tensor core, then compose the shares ------------------
         // `full` completes when a tile's MMAs have written TMEM; `drained` when all 128 threads have
         // read their lane out of it, so thread 0 can launch the next tile's MMAs under everyone's
         // (and its own) compose arithmetic instead of after a CTA-wide barrier.
-        if (tid == 0) issue_tile<S>(taddr, a_base, b_base, full_bar);
 #pragma unroll 1
         for (int q = 0; q < S::G; q++) {
             mbar_wait(full_bar, parity);
@@ -237,23 +301,30 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
+#if SDA_TC_PREFETCH == 1
+            // next pass's secrets: issued under the last tile's compose arithmetic, consumed after it
+            if (q == S::G - 1 && more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
+#endif
             if (tid == 0 && q + 1 < S::G) {
                 mbar_wait(drained_bar, parity);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_tile<S>(taddr, a_base + (q + 1) * S::A_TILE, b_base, full_bar);
+                issue_tile<S>(taddr, d_cur + (q + 1) * S::D_TILE, s_base + (q + 1) * S::S_TILE, b_base, full_bar);
             }
             parity ^= 1;
             const size_t b = b_base_batch + (size_t)q * CTA + tid;
-            int64_t *ob = out + p * (size_t)N * B + b;
+            char *ob = reinterpret_cast<char *>(out + p * (size_t)N * B + b);
+            const bool live = b < B;
 #pragma unroll
             for (int j = 0; j < N; j++) {
                 const uint64_t r = compose(d[j], two16);
-                if (b < B) *ob = (int64_t)r;
-                ob += B;
+                if (live) *reinterpret_cast<int64_t *>(ob + (size_t)j * row_bytes) = (int64_t)r;
             }
         }
-        // every thread is past its TMEM loads of the last tile, and every MMA of this pass has completed
-        // (full was waited on): the staging barrier of the next pass orders the rest
+        // every thread is past its TMEM loads of the last tile and every MMA of this pass has completed
+        // (`full` was waited on), so the next pass may overwrite the secrets and reuse TMEM
+        p = pn;
+        u = un;
+        buf ^= 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -267,24 +338,21 @@ void build_b_image(const Matrix &m, uint8_t *img) {
     typedef unsigned __int128 u128;
     memset(img, 0, S::B_BYTES);
     for (int j = 0; j < N; j++)
-        for (int c = 0; c < S::C; c++)
-            for (int v = 0; v < 2; v++) {
-                int xi;                                    // index into x = [secrets ; randomness]
-                if (c < S::DC) {
-                    if (2 * c + v >= T) continue;
-                    xi = K + 2 * c + v;
-                } else {
-                    if (2 * (c - S::DC) + v >= K) continue;
-                    xi = 2 * (c - S::DC) + v;
-                }
-                for (int byte = 0; byte < 8; byte++) {
-                    const uint64_t cst = (uint64_t)((u128)m.e[j * (K + T) + xi] * ((((u128)1) << (8 * byte)) % P61) % P61);
-                    for (int s = 0; s < 8; s++) {
-                        const int n = j * 8 + s;
-                        img[(n / 8) * S::SBO_B + c * LBO + (n % 8) * 16 + v * 8 + byte] = (uint8_t)(cst >> (8 * s));
+        for (int part = 0; part < 2; part++)                // 0: draws (K steps 0..NKD), 1: secrets (the rest)
+            for (int c = 0; c < (part ? S::SC : S::DC); c++)
+                for (int v = 0; v < 2; v++) {
+                    const int idx = 2 * c + v;                  // draw / secret index within the batch
+                    if (idx >= (part ? K : T)) continue;
+                    const int xi = part ? idx : K + idx;        // index into x = [secrets ; randomness]
+                    const int cg = part ? 2 * S::NKD + c : c;   // chunk along K of the whole row
+                    for (int byte = 0; byte < 8; byte++) {
+                        const uint64_t cst = (uint64_t)((u128)m.e[j * (K + T) + xi] * ((((u128)1) << (8 * byte)) % P61) % P61);
+                        for (int s = 0; s < 8; s++) {
+                            const int n = j * 8 + s;
+                            img[(n / 8) * S::SBO_B + cg * LBO + (n % 8) * 16 + v * 8 + byte] = (uint8_t)(cst >> (8 * s));
+                        }
                     }
                 }
-            }
 }
 
 template <int K, int T, int N, int ROUNDS>
@@ -294,7 +362,7 @@ cudaError_t launch(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_
     const size_t B = (dim + K - 1) / K;
     const size_t units_per_p = (B + S::G * CTA - 1) / (S::G * CTA);
     const size_t units_total = units_per_p * P;
-    const size_t smem = ((S::A_BYTES + 127) & ~127u) + S::B_BYTES;
+    const size_t smem = S::SMEM;
     auto kern = packed_share_tc_kernel<K, T, N, ROUNDS>;
     static int per_sm = 0;      // resident CTAs per SM: every one of them must hold its TMEM columns
     if (per_sm == 0) {

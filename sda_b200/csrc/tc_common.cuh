@@ -77,7 +77,7 @@ __device__ __forceinline__ uint64_t compose(const uint32_t (&d)[8], uint32_t two
     return pack(r_lo, r_hi & LOW29);
 }
 
-__device__ __forceinline__ uint64_t canon_negative(int64_t v) {                 // v < 0 -> [0, p)
+static __device__ __noinline__ uint64_t canon_negative(int64_t v) {                 // v < 0 -> [0, p)
     const uint64_t a = 0ull - (uint64_t)v;
     uint64_t r = (a & P61) + (a >> 61);
     r = r >= P61 ? r - P61 : r;

@@ -58,6 +58,52 @@ double sm_clock_mhz() {
     return (double)h[0] / (double)h[1] * 1e3;
 }
 
+
+// rotate implemented on the FMA pipe: lo = x << r (IMAD.SHL), rot = hi32(x * 2^r) + lo (IMAD.HI.U32)
+template <int MODE>
+__global__ void __launch_bounds__(256) rotk(uint64_t *out, uint32_t a, uint32_t b) {
+    uint32_t x[8];
+    for (int i = 0; i < 8; i++) x[i] = a + i * 7 + threadIdx.x;
+#pragma unroll 1
+    for (int it = 0; it < N_ITER; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (MODE == 0) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i % 8]) : "r"(b), "r"(a));
+            if (MODE == 1) asm volatile("{.reg .u32 t; mul.lo.u32 t, %0, %1; mad.hi.u32 %0, %0, %1, t;}" : "+r"(x[i % 8]) : "r"(b));
+            if (MODE == 2) asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(x[i % 8]));
+            if (MODE == 3) {   // half the rotates on each pipe + one xor each (ChaCha-like mix)
+                if (i & 1) asm volatile("{.reg .u32 t; mul.lo.u32 t, %0, %1; mad.hi.u32 %0, %0, %1, t;}" : "+r"(x[i % 8]) : "r"(b));
+                else asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(x[i % 8]));
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[i % 8]) : "r"(a));
+            }
+            if (MODE == 4) {   // all rotates on the ALU pipe + one xor each
+                asm volatile("shf.l.wrap.b32 %0, %0, %0, 7;" : "+r"(x[i % 8]));
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(x[i % 8]) : "r"(a));
+            }
+        }
+    }
+    uint64_t s = 0;
+    for (int i = 0; i < 8; i++) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+template <int MODE>
+void run_rot(const char *name, int ctas_per_sm) {
+    uint64_t *out;
+    const int sms = 148;
+    cudaMalloc(&out, sizeof(uint64_t) * 256 * sms * ctas_per_sm);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    rotk<MODE><<<sms * ctas_per_sm, 256>>>(out, 3, 128);
+    cudaEventRecord(e0);
+    rotk<MODE><<<sms * ctas_per_sm, 256>>>(out, 3, 128);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double cyc = ms * 1e-3 * sm_clock_mhz() * 1e6;
+    const double steps = (double)N_ITER * 16 * (8.0 * ctas_per_sm / 4.0);
+    printf("%-44s ctas/SM=%d  cycles per inner step per SMSP: %.2f\n", name, ctas_per_sm, cyc / steps);
+    cudaFree(out);
+}
+
 template <int NW, int NA, int NI>
 void run(const char *name, int split, int ctas_per_sm) {
     uint64_t *out;
@@ -93,6 +139,13 @@ int main() {
         run<8, 16, 0>("split warps: wide 8 | alu 16", 1, c);
         run<8, 32, 0>("split warps: wide 8 | alu 32", 1, c);
         run<0, 16, 16>("split warps: imad 16 | alu 16", 1, c);
+    }
+    for (int c : {4}) {
+        run_rot<0>("mad.hi.u32 (IMAD.HI)", c);
+        run_rot<1>("rotate = mul.lo + mad.hi (2 FMA-pipe)", c);
+        run_rot<2>("rotate = shf (ALU)", c);
+        run_rot<3>("xor + rotate, rotates split ALU/FMA 1:1", c);
+        run_rot<4>("xor + rotate, all ALU", c);
     }
     return 0;
 }
