@@ -205,7 +205,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import sda_b200
-    from sda_b200 import params
+    from sda_b200 import multi, params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,10 +248,10 @@ def run_ours(args):
             for cl in range(n):
                 ctx.share_combine_dev(scheme, d_sh[:, cl, :], n * B, T, B, d_sum[cl])
             if world > 1:
-                # canonical partials < p: the uint64 sum of <= 8 of them cannot wrap
-                dist.reduce(d_sum, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    ctx.mod_reduce_dev(p, d_sum, n * B, d_tot, unsigned=True)
+                # one collective: canonical partials < p summed as 64-bit integers (<= 8 of them cannot wrap),
+                # then one mod-p pass on the root (sda_b200/multi.py, tests/test_multi_gloo.py)
+                multi.reduce_partial_sums(d_sum, p, dst=0,
+                                          final_mod=lambda t: ctx.mod_reduce_dev(p, t, n * B, d_tot, unsigned=True))
             c.record(stream)
             if timed:
                 return a, b, c
@@ -281,6 +281,48 @@ def run_ours(args):
             gen_ms.append(a.elapsed_time(b))
             comb_ms.append(b.elapsed_time(c))
         kernel_name = ctx.last_kernel()
+
+        # the same share-gen launch at the other keystream round counts the context offers (not part of
+        # `value`: the sharing randomness replaces the reference's OsRng, the round count is a context option)
+        other_rounds = {}
+        if rank == 0 and not args.no_round_sweep:
+            for r in (12, 8):
+                if r == args.rounds:
+                    continue
+                ctx.set_rng_rounds(r)
+                ctx.share_generate_dev(scheme, d_sec, dim, T, dim, seeds_for(-100 - r, rank, T), d_sh)
+                ts = []
+                for i in range(3):
+                    a, b = ev(), ev()
+                    a.record(stream)
+                    ctx.share_generate_dev(scheme, d_sec, dim, T, dim, seeds_for(-200 - r - i, rank, T), d_sh)
+                    b.record(stream)
+                    ctx.synchronize()
+                    ts.append(a.elapsed_time(b))
+                other_rounds[r] = statistics.median(ts)
+            ctx.set_rng_rounds(args.rounds)
+
+        # the fused participant -> clerk kernel: same clerk sums without materialising the
+        # shares, the participant sum accumulated in TMEM.  Checked against the K2 + K3 result, then timed.
+        fused_ms = None
+        if rank == 0 and not args.no_round_sweep:
+            sd = seeds_for(-300, rank, T)
+            ctx.share_generate_dev(scheme, d_sec, dim, T, dim, sd, d_sh)
+            for cl in range(n):
+                ctx.share_combine_dev(scheme, d_sh[:, cl, :], n * B, T, B, d_sum[cl])
+            ctx.share_generate_combine_dev(scheme, d_sec, dim, T, dim, sd, d_tot)
+            ctx.synchronize()
+            if not torch.equal(d_tot, d_sum):
+                raise SystemExit("bench self-check failed: fused share-gen+clerk-sum != share-gen then combine")
+            ts = []
+            for i in range(3):
+                a, b = ev(), ev()
+                a.record(stream)
+                ctx.share_generate_combine_dev(scheme, d_sec, dim, T, dim, seeds_for(-310 - i, rank, T), d_tot)
+                b.record(stream)
+                ctx.synchronize()
+                ts.append(a.elapsed_time(b))
+            fused_ms = statistics.median(ts)
 
         # correctness spot check of what was just timed (cheap, outside the timed region):
         # reveal(clerk sums) == column sums of the secrets
@@ -356,7 +398,15 @@ def run_ours(args):
                 "share_of_step": gen_avg_ms / (gen_avg_ms + comb_avg_ms)}
     kernels = {
         "share_gen": {"ms": gen_avg_ms, "elements_per_s": T * dim / (gen_avg_ms * 1e-3), "GBps": achieved,
-                      "frac_of_hbm": achieved / peak},
+                      "frac_of_hbm": achieved / peak, "rng_rounds": args.rounds},
+        **{f"share_gen_chacha{r}": {"ms": ms, "elements_per_s": T * dim / (ms * 1e-3), "GBps": alg_bytes / (ms * 1e-3) / 1e9,
+                                    "frac_of_hbm": alg_bytes / (ms * 1e-3) / 1e9 / peak, "rng_rounds": r}
+           for r, ms in other_rounds.items()},
+        **({"fused_share_gen_clerk_sum": {"ms": fused_ms, "elements_per_s": T * dim / (fused_ms * 1e-3),
+                                          "GBps": T * dim * 8 / (fused_ms * 1e-3) / 1e9,
+                                          "frac_of_hbm": T * dim * 8 / (fused_ms * 1e-3) / 1e9 / peak,
+                                          "note": "sda_share_generate_combine_dev: reads 8 B per secret, shares never "
+                                                  "materialised; not part of `value`"}} if fused_ms else {}),
         "clerk_combine_x5": {"ms": comb_avg_ms, "share_elements_per_s": n * T * B / (comb_avg_ms * 1e-3),
                              "GBps": comb_bytes / (comb_avg_ms * 1e-3) / 1e9,
                              "frac_of_hbm": comb_bytes / (comb_avg_ms * 1e-3) / 1e9 / peak,
@@ -406,6 +456,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--no-round-sweep", action="store_true", help="skip the ChaCha12/ChaCha8 share-gen launches")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="target CPU seconds per reference step")
     ap.add_argument("--ref-dim", type=int, default=500_000)
     args = ap.parse_args()

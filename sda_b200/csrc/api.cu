@@ -394,6 +394,21 @@ int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
     return SDA_OK;
 }
 
+// the constant GEMM operand of the tensor-core share-generation kernels, resident on the device per scheme
+int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
+    const size_t ib = packed_share_tc_image_bytes(pk.k, pk.t, pk.n);
+    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n};
+    key.insert(key.end(), M.e, M.e + M.rows * M.cols);
+    if (key == ctx->tc_image_key) return SDA_OK;
+    std::vector<uint8_t> img(ib);
+    packed_share_tc_build_image(pk.k, pk.t, pk.n, M, img.data());
+    CU(ctx->tc_image.reserve(ib));
+    CU(cudaMemcpyAsync(ctx->tc_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
+    ctx->tc_image_key = key;
+    return SDA_OK;
+}
+
 // ---- core device-side operations (shared by host and device entry points) --------------------
 
 int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t ld, size_t P,
@@ -427,17 +442,7 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     const bool use_tc = !additive && fast && f.kind == FIELD_MERSENNE61 && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
                         packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0;
     if (use_tc) {
-        const size_t ib = packed_share_tc_image_bytes(pk.k, pk.t, pk.n);
-        std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n};
-        key.insert(key.end(), M.e, M.e + M.rows * M.cols);
-        if (key != ctx->tc_image_key) {
-            std::vector<uint8_t> img(ib);
-            packed_share_tc_build_image(pk.k, pk.t, pk.n, M, img.data());
-            CU(ctx->tc_image.reserve(ib));
-            CU(cudaMemcpyAsync(ctx->tc_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
-            ctx->tc_image_key = key;
-        }
+        OK(ensure_tc_image(ctx, pk, M));
         OK(clear_flags(ctx));
         CU(launch_packed_share_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, d_keys,
                                   (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
@@ -814,6 +819,26 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
         else if (!d_acc_in)
             CU(cudaMemsetAsync(d_out, 0, n * B * sizeof(int64_t), ctx->stream));
         return SDA_OK;
+    }
+    // Mersenne-61 fast shapes: one fused kernel, the participant sum accumulated in TMEM (packed_tc.cu)
+    if (s->kind == SDA_SHARING_PACKED_SHAMIR && (uint64_t)s->modulus == P61 && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES) {
+        Packed pk;
+        OK(validate(ctx, s, &pk));
+        if (packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
+            if (!seeds) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
+            Matrix M;
+            OK(share_matrix(ctx, pk, &M));
+            OK(ensure_tc_image(ctx, pk, M));
+            OK(upload_keys(ctx, seeds, P));
+            OK(clear_flags(ctx));
+            CU(launch_packed_share_combine_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
+                                              (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_acc_in,
+                                              d_out, ctx->d_flag));
+            unsigned rejected = 0;
+            OK(read_flags(ctx, &rejected, nullptr));
+            if (!rejected) return SDA_OK;
+            // a rejected gen_range word somewhere (p ~ 2^-57 per draw): redo on the materialising path below
+        }
     }
     // tiles of participants: generate [tile][n][B] into ctx->aux, fold each clerk's rows into out
     const size_t per = n * B * sizeof(int64_t);

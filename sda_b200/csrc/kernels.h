@@ -89,6 +89,10 @@ void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint8_t
 cudaError_t launch_packed_share_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                    size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
                                    int64_t *shares_out, unsigned *flag);
+// fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
+cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
+                                           size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
+                                           const int64_t *acc_in, int64_t *out, unsigned *flag);
 // true when launch_packed_share / launch_additive_split have an in-kernel-rng instantiation
 bool packed_share_has_fast_path(int k, int t, int n);
 bool additive_split_has_fast_path(int n);

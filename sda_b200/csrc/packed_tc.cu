@@ -59,6 +59,7 @@ constexpr int gcd_c(int a, int b) { return b == 0 ? a : gcd_c(b, a % b); }
 template <int K, int T, int N>
 struct Shape {
     static_assert(T % 2 == 0 && T >= 2, "draws fill whole 16-byte chunks");
+    static constexpr int kT = T;
     static constexpr int G = 8 / gcd_c(T, 8);              // 128-batch tiles per pass of a CTA
     static constexpr int NB = T / gcd_c(T, 8);             // keystream blocks per thread per pass
     // A row = [draws | secrets]; the two parts live in separate buffers (the draws double-buffered, so the
@@ -331,6 +332,212 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(S::TMEM_COLS) : "memory");
 }
 
+// =================================================================================================
+// Fused participant -> clerk path (the reference's FIXME at client/src/clerk.rs:71-72):
+//     out[j][b] = acc_in[j][b] + sum_p share_j(participant p, batch b)   (mod p)
+// without ever materialising shares[P][n][B].  The GEMM formulation makes the sum free: a tile of 128
+// batches is multiplied for participant after participant INTO THE SAME TMEM ACCUMULATOR (tcgen05.mma
+// with accumulate), so the eight limb sums of every share simply keep growing -- at most 96 * 255^2 per
+// participant, i.e. 256 participants fit the s32 accumulators -- and the per-share compose arithmetic runs
+// once per 256 participants instead of once per participant.  What is left per participant is the
+// keystream, the staging of the rows and one MMA.
+//
+// A CTA owns batch range r (128 batches) and walks the participants four at a time: warp w produces the
+// keystream of participant p + w for the range (16 T blocks per tile = T / 2 per lane), thread tid stages
+// the secrets of batch r * 128 + tid of all four, and the four tiles are four MMA groups on one accumulator.
+template <int K, int T, int N>
+struct FusedShape : Shape<K, T, N> {
+    typedef Shape<K, T, N> S;
+    static constexpr int GP = 4;                               // participants per pass (one per warp)
+    static constexpr int NBW = T / 2;                          // keystream blocks per lane per pass
+    static constexpr uint32_t D_BYTES = GP * S::D_TILE + 128, S_BYTES = GP * S::S_TILE + 128;
+    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + S::B_BYTES;
+    static constexpr int TMEM_COLS = S::NMMA <= 32 ? 32 : S::NMMA <= 64 ? 64 : 128;
+    static constexpr int MAX_ACCUM = 256;                      // participants per TMEM accumulation: 256 * 96 * 255^2 < 2^31
+};
+
+// limb sums d[s] < 2^31 -> canonical sum_s d[s] 2^{8s} mod p (runs once per 256 participants: clarity over speed)
+__device__ __forceinline__ uint64_t compose_wide(const uint32_t (&d)[8]) {
+    uint64_t lo = 0, hi = 0;                                   // value = lo + hi 2^32, both < 2^57
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        lo += (uint64_t)d[s] << (8 * s);
+        hi += (uint64_t)d[4 + s] << (8 * s);
+    }
+    // hi 2^32 = (hi mod 2^29) 2^32 + (hi >> 29) 2^61 == (hi mod 2^29) 2^32 + (hi >> 29)
+    uint64_t v = lo + ((hi & LOW29) << 32) + (hi >> 29);       // < 2^57 + 2^61 + 2^28
+    v = (v & P61) + (v >> 61);
+    return v >= P61 ? v - P61 : v;
+}
+
+template <class F, int ROUNDS>
+__device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ keys, size_t p, size_t r, int warp, int lane,
+                                                  uint8_t *sD, unsigned *flag) {
+    typedef typename F::S S;
+    uint32_t k[8];
+    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
+    const uint4 ka = __ldg(src), kb = __ldg(src + 1);
+    k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
+    k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
+#pragma unroll 1
+    for (int nb = 0; nb < F::NBW; nb++) {
+        const uint32_t blk = nb * 32 + lane;                       // block of this tile, in stream order
+        uint32_t w[16];
+        chacha_block<ROUNDS>(k, r * (size_t)(16 * S::kT) + blk, w);
+        uint32_t suspect = 0;
+#pragma unroll
+        for (int cb = 0; cb < 4; cb++) {
+            const uint64_t xa = reduce_draw(w[4 * cb], w[4 * cb + 1], suspect);
+            const uint64_t xb = reduce_draw(w[4 * cb + 2], w[4 * cb + 3], suspect);
+            const uint32_t gc = blk * 4 + cb;                      // chunk index of the tile
+            const uint32_t row = gc / S::DC, c = gc % S::DC;
+            uint32_t xal, xah, xbl, xbh;
+            unpack(xa, xal, xah);
+            unpack(xb, xbl, xbh);
+            *reinterpret_cast<uint4 *>(sD + warp * S::D_TILE + (row >> 3) * S::SBO_D + c * LBO + (row & 7) * 16) =
+                make_uint4(xal, xah, xbl, xbh);
+        }
+        if (suspect & (1u << 29)) {
+            bool bad = false;
+#pragma unroll
+            for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;
+            if (bad) atomicOr(flag, 1u);
+        }
+    }
+}
+
+template <int K, int T, int N, int ROUNDS>
+__global__ void __launch_bounds__(CTA)
+packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t P,
+                               const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
+                               const int64_t *__restrict__ acc_in, int64_t *__restrict__ out, unsigned *flag) {
+    typedef FusedShape<K, T, N> F;
+    typedef Shape<K, T, N> S;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *sD = smem;                                    // 2 x (4 participants x 128 rows x draws)
+    uint8_t *sS = smem + 2 * F::D_BYTES;                   // 4 participants x 128 rows x secrets
+    uint8_t *sB = sS + F::S_BYTES;
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&tmem_base)), "n"(F::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < S::B_BYTES / 16; i += CTA) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base;
+    const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
+    const uint32_t full_bar = smem_u32(&mbar);
+    const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
+    uint32_t parity = 0, buf = 0;
+
+    const size_t ranges = (B + CTA - 1) / CTA;
+    const size_t groups = (P + F::GP - 1) / F::GP;
+    // keystream of the first pass
+    if (blockIdx.x < ranges && (size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+
+    for (size_t r = blockIdx.x; r < ranges; r += gridDim.x) {
+        const size_t b = r * CTA + tid;                    // this thread's batch
+        const size_t e0 = b * K;
+        uint64_t acc[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            int64_t a = (acc_in != nullptr && b < B) ? acc_in[(size_t)j * B + b] : 0;
+            if (a < 0) a = (int64_t)canon_negative(a);
+            acc[j] = (uint64_t)a >= P61 ? (((uint64_t)a & P61) + ((uint64_t)a >> 61)) % P61 : (uint64_t)a;
+        }
+        int in_tmem = 0;                                   // participants accumulated in TMEM since the last drain
+        for (size_t g = 0; g < groups; g++) {
+            const size_t p0 = g * F::GP;
+            const int np = (int)(P - p0 < (size_t)F::GP ? P - p0 : F::GP);
+            // ---- secrets of batch b of the np participants: their bytes are the limbs -----------
+#pragma unroll
+            for (int q = 0; q < F::GP; q++) {
+                if (q < np) {
+                    const int64_t *sec = secrets + (p0 + q) * ld;
+                    int64_t s[2 * S::SC];
+#pragma unroll
+                    for (int i = 0; i < 2 * S::SC; i++) s[i] = (i < K && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+#pragma unroll
+                    for (int i = 0; i < K; i++)
+                        if (s[i] < 0) s[i] = (int64_t)canon_negative(s[i]);
+#pragma unroll
+                    for (int c = 0; c < S::SC; c++) {
+                        uint32_t al, ah, bl, bh;
+                        unpack((uint64_t)s[2 * c], al, ah);
+                        unpack((uint64_t)s[2 * c + 1], bl, bh);
+                        *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) =
+                            make_uint4(al, ah, bl, bh);
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (tid == 0) {
+                const uint32_t d_cur = d_base + buf * F::D_BYTES;
+                const uint64_t db = umma_desc(b_base, S::SBO_B);
+                for (int q = 0; q < np; q++) {
+                    const uint64_t dd = umma_desc(d_cur + q * S::D_TILE, S::SBO_D), ds = umma_desc(s_base + q * S::S_TILE, S::SBO_S);
+#pragma unroll
+                    for (int kk = 0; kk < S::NKD; kk++)
+                        umma_i8(taddr, dd + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S::IDESC, (in_tmem + q + kk) > 0);
+#pragma unroll
+                    for (int kk = 0; kk < S::NKS; kk++)
+                        umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
+            }
+            in_tmem += np;
+            // ---- the next pass's keystream (next participants of this range, or the next range) under the MMAs
+            {
+                size_t rn = r, pn = p0 + F::GP + warp;
+                if (g + 1 == groups) {
+                    rn = r + gridDim.x;
+                    pn = warp;
+                }
+                if (rn < ranges && pn < P) stage_draws_fused<F, ROUNDS>(keys, pn, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
+            }
+            mbar_wait(full_bar, parity);                   // rows consumed: the next pass may overwrite the secrets
+            parity ^= 1;
+            buf ^= 1;
+            // ---- drain TMEM when the accumulators are about to fill up, and at the end of the range -------
+            if (in_tmem + F::GP > F::MAX_ACCUM || g + 1 == groups) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    uint32_t d[8];
+                    tmem_ld8(my_taddr + 8 * j, d);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const uint64_t v = acc[j] + compose_wide(d);
+                    acc[j] = v >= P61 ? v - P61 : v;
+                }
+                in_tmem = 0;
+                // the next MMA (accumulate = 0) is issued after the next staging barrier, which every thread
+                // reaches only after these loads
+            }
+        }
+        if (b < B) {
+#pragma unroll
+            for (int j = 0; j < N; j++) out[(size_t)j * B + b] = (int64_t)acc[j];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(F::TMEM_COLS) : "memory");
+}
+
 // the constant operand as it lies in shared memory
 template <int K, int T, int N>
 void build_b_image(const Matrix &m, uint8_t *img) {
@@ -394,6 +601,40 @@ cudaError_t dispatch(const LaunchCtx &lc, int rounds, const int64_t *secrets, si
 
 }  // namespace
 
+template <int K, int T, int N, int ROUNDS>
+cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                         const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
+    typedef FusedShape<K, T, N> F;
+    const size_t B = (dim + K - 1) / K;
+    const size_t ranges = (B + CTA - 1) / CTA;
+    const size_t smem = F::SMEM;
+    auto kern = packed_share_combine_tc_kernel<K, T, N, ROUNDS>;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncAttributes fa;
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * CTA);
+        const int by_smem = (int)((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
+        per_sm = std::max(1, std::min(by_regs, std::min(by_smem, 512 / F::TMEM_COLS)));
+    }
+    const size_t grid = std::min<size_t>(ranges, (size_t)lc.sm_count * per_sm);
+    kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, P, keys, reinterpret_cast<const uint4 *>(d_b_image),
+                                                   acc_in, out, flag);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+template <int K, int T, int N>
+cudaError_t dispatch_fused(const LaunchCtx &lc, int rounds, const int64_t *secrets, size_t ld, size_t P, size_t dim,
+                           const ChaChaKey *keys, const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
+    if (rounds == 8) return launch_fused<K, T, N, 8>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
+    if (rounds == 12) return launch_fused<K, T, N, 12>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
+    return launch_fused<K, T, N, 20>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
+}
+
 #define SDA_TC_SHAPES(X) X(3, 2, 5) X(5, 4, 9) X(3, 4, 7) X(3, 4, 8)
 
 size_t packed_share_tc_image_bytes(int k, int t, int n) {
@@ -417,6 +658,20 @@ cudaError_t launch_packed_share_tc(const LaunchCtx &lc, int rounds, int k, int t
     if (k == K && t == T && n == N) {                                                                     \
         *lc.kernel_name = "packed_share<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8";           \
         return dispatch<K, T, N>(lc, rounds, secrets, ld, P, dim, keys, d_b_image, shares_out, flag);     \
+    }
+    SDA_TC_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+// fused share generation + clerk accumulation over the participants: out[n][B] = acc_in + sum_p shares(p)
+cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
+                                           size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
+                                           const int64_t *acc_in, int64_t *out, unsigned *flag) {
+#define X(K, T, N)                                                                                              \
+    if (k == K && t == T && n == N) {                                                                           \
+        *lc.kernel_name = "packed_share_combine<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8, TMEM-accumulated"; \
+        return dispatch_fused<K, T, N>(lc, rounds, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);    \
     }
     SDA_TC_SHAPES(X)
 #undef X

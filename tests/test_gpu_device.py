@@ -130,6 +130,32 @@ def test_share_generate_combine_dev(ctx, oracle, torch_cuda):
         assert np.array_equal(host(out), exp)
 
 
+@pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
+def test_fused_share_generate_combine_tmem_accumulation(ctx, oracle, torch_cuda, mk):
+    """the fused tensor-core kernel sums the participants inside TMEM (drained every 256): participant counts
+    around the pass (4) and drain (256) boundaries, a running sum passed in, ranges ending inside a tile,
+    negative secrets"""
+    t = torch_cuda
+    s = mk()
+    k, n, m = s.input_size(), s.output_size(), s.modulus
+    rng = np.random.default_rng(21)
+    for P, dim in [(1, 5), (3, 128 * k), (4, 129 * k + 1), (7, 1000), (258, 300 * k), (515, 130)]:
+        B = s.batches(dim)
+        secrets = rng.integers(0, m, size=(P, dim), dtype=np.int64)
+        secrets[0, ::3] = rng.integers(-(1 << 63), 1 << 63, size=secrets[0, ::3].shape, dtype=np.int64)
+        seeds = b"".join(util.seed_bytes(f"fused/{P}/{dim}/{pi}") for pi in range(P))
+        acc_in = rng.integers(0, m, size=(n, B), dtype=np.int64)
+        out = t.empty((n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_combine_dev(s, dev(t, secrets), dim, P, dim, seeds, out, d_acc_in=dev(t, acc_in))
+        ctx.synchronize()
+        assert "TMEM-accumulated" in ctx.last_kernel()
+        total = acc_in.astype(object)
+        for pi in range(P):
+            sh = util.canon(oracle, m, util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True))
+            total = total + sh.astype(object)
+        assert np.array_equal(host(out), (total % m).astype(np.int64)), (P, dim)
+
+
 def test_mod_reduce_and_unmask_dev(ctx, oracle, torch_cuda):
     t = torch_cuda
     rng = np.random.default_rng(6)

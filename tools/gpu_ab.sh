@@ -4,5 +4,5 @@ mkdir -p gpurun_out
 r=$1; shift
 for lib in "$@"; do
   name=$(basename $lib .so)
-  SDA_B200_LIB=$PWD/$lib timeout 300 python bench.py --rounds $r --packed-path tc --no-e2e --no-cpu-baseline > gpurun_out/ab_${name}_r$r.json 2> gpurun_out/ab_${name}_r$r.err
+  SDA_B200_LIB=$PWD/$lib timeout 300 python bench.py --rounds $r --packed-path tc --no-e2e --no-cpu-baseline --no-round-sweep > gpurun_out/ab_${name}_r$r.json 2> gpurun_out/ab_${name}_r$r.err
 done
