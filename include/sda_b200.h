@@ -205,6 +205,20 @@ int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_
 int sda_unmask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_mask, const int64_t *d_masked,
                    size_t dim, int64_t *d_out);
 
+/* ---- share wire codec: the step either side of the path ------------------------------------ */
+/* ShareEncryptor::encrypt's encoding loop (client/src/crypto/encryption/sodium.rs:35-41) and
+ * ShareDecryptor::decrypt's decoding loop (sodium.rs:83-90): `integer-encoding 1.0` varints, i.e.
+ * zig-zag then unsigned LEB128, values concatenated without a count.  The sealed box around the
+ * bytes stays with libsodium.  `out` of encode needs sda_varint_max_bytes(n) = 10 n bytes.
+ * decode fails with SDA_ERR_INVALID on a stream that ends inside a value, holds a value longer than
+ * 10 bytes (the reference's decode_var would read past a u64 there), or holds more than `cap` values. */
+size_t sda_varint_max_bytes(size_t n);
+int sda_varint_encode(sda_ctx *ctx, const int64_t *shares, size_t n, uint8_t *out, size_t *out_len);
+int sda_varint_decode(sda_ctx *ctx, const uint8_t *buf, size_t len, int64_t *shares_out, size_t cap, size_t *n);
+/* device buffers; the length / count comes back through a host pointer (one stream synchronisation) */
+int sda_varint_encode_dev(sda_ctx *ctx, const int64_t *d_shares, size_t n, uint8_t *d_out, size_t *out_len);
+int sda_varint_decode_dev(sda_ctx *ctx, const uint8_t *d_buf, size_t len, int64_t *d_shares_out, size_t cap, size_t *n);
+
 /* Synthetic benchmark / test inputs, generated on the device: out[i] = value(start + i) where
  * value(e) = u64 draw e of ChaCha20(key "sda-b200-synthetic-v1", key word 7 = stream) mod m.
  * Same definition as the oracle's sdao_synth_fill. */

@@ -73,6 +73,11 @@ PROTOTYPES = {
     "sda_mask_dev": (_int, [_vp, _ms, _vp, _sz, _vp, _vp, _vp]),
     "sda_mask_combine_dev": (_int, [_vp, _ms, _vp, _sz, _sz, _vp]),
     "sda_unmask_dev": (_int, [_vp, _ms, _vp, _vp, _sz, _vp]),
+    "sda_varint_max_bytes": (_sz, [_sz]),
+    "sda_varint_encode": (_int, [_vp, _vp, _sz, _vp, _psz]),
+    "sda_varint_decode": (_int, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "sda_varint_encode_dev": (_int, [_vp, _vp, _sz, _vp, _psz]),
+    "sda_varint_decode_dev": (_int, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "sda_synth_fill_dev": (_int, [_vp, C.c_uint32, _i64, _u64, _sz, _vp]),
 }
 

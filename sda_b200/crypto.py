@@ -324,6 +324,35 @@ class Context:
         self.check(self._lib.sda_unmask_dev(self._h, C.byref(scheme.c), _dev_ptr(d_mask), _dev_ptr(d_masked), dim,
                                             _dev_ptr(d_out)))
 
+    # -- share wire codec (encryption/sodium.rs:35-41, 83-90) --------------------------------------
+    def varint_encode(self, shares):
+        """`for share in shares { share.encode_var(..) }`: zig-zag LEB128, concatenated.  Returns uint8 array."""
+        v = _i64(shares)
+        out = np.empty(max(10 * len(v), 1), dtype=np.uint8)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_varint_encode(self._h, _ptr(v), len(v), _ptr(out), C.byref(n)))
+        return out[:n.value]
+
+    def varint_decode(self, buf, cap=None):
+        """`while !reader.is_empty() { Share::decode_var(reader) }`.  Returns int64 array."""
+        b = np.ascontiguousarray(np.frombuffer(bytes(buf), dtype=np.uint8)) if not isinstance(buf, np.ndarray) \
+            else np.ascontiguousarray(buf, dtype=np.uint8)
+        cap = len(b) if cap is None else cap
+        out = np.empty(max(cap, 1), dtype=np.int64)
+        n = C.c_size_t(0)
+        self.check(self._lib.sda_varint_decode(self._h, _ptr(b), len(b), _ptr(out), cap, C.byref(n)))
+        return out[:n.value]
+
+    def varint_encode_dev(self, d_shares, n, d_out):
+        ln = C.c_size_t(0)
+        self.check(self._lib.sda_varint_encode_dev(self._h, _dev_ptr(d_shares), n, _dev_ptr(d_out), C.byref(ln)))
+        return ln.value
+
+    def varint_decode_dev(self, d_buf, length, d_out, cap):
+        cnt = C.c_size_t(0)
+        self.check(self._lib.sda_varint_decode_dev(self._h, _dev_ptr(d_buf), length, _dev_ptr(d_out), cap, C.byref(cnt)))
+        return cnt.value
+
     def synth_fill_dev(self, stream_id, modulus, start, count, d_out):
         self.check(self._lib.sda_synth_fill_dev(self._h, stream_id, modulus, start, count, _dev_ptr(d_out)))
 

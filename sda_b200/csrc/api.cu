@@ -933,6 +933,70 @@ int sda_unmask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_m
     return SDA_OK;
 }
 
+// ---- share wire codec ----------------------------------------------------------------------------
+size_t sda_varint_max_bytes(size_t n) { return 10 * n; }
+
+int sda_varint_encode_dev(sda_ctx *ctx, const int64_t *d_shares, size_t n, uint8_t *d_out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    const size_t se = varint_encode_scratch_elems(n);
+    CU(ctx->scratch.reserve(se * sizeof(uint64_t)));
+    CU(launch_varint_encode(ctx->lc(), d_shares, n, d_out, (uint64_t *)ctx->scratch.p));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, (uint64_t *)ctx->scratch.p + (se - 1), sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (out_len) *out_len = (size_t)total;
+    return SDA_OK;
+}
+
+int sda_varint_decode_dev(sda_ctx *ctx, const uint8_t *d_buf, size_t len, int64_t *d_shares_out, size_t cap, size_t *n) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    const size_t se = varint_decode_scratch_elems(len);
+    CU(ctx->scratch.reserve(se * sizeof(uint64_t)));
+    OK(clear_flags(ctx));
+    CU(launch_varint_decode(ctx->lc(), d_buf, len, d_shares_out, cap, (uint64_t *)ctx->scratch.p, ctx->d_flag));
+    uint64_t total = 0;
+    CU(cudaMemcpyAsync(&total, (uint64_t *)ctx->scratch.p + (se - 1), sizeof total, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned status = 0;
+    OK(read_flags(ctx, &status, nullptr));     // synchronises the stream
+    if (n) *n = (size_t)total;
+    if (status & 2u) return fail(ctx, SDA_ERR_INVALID, "varint stream ends inside a value");
+    if (status & 1u) return fail(ctx, SDA_ERR_INVALID, "varint value longer than 10 bytes");
+    if (status & 4u) return fail(ctx, SDA_ERR_INVALID, "varint stream holds %llu values, capacity %zu", (unsigned long long)total, cap);
+    return SDA_OK;
+}
+
+int sda_varint_encode(sda_ctx *ctx, const int64_t *shares, size_t n, uint8_t *out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (out_len) *out_len = 0;
+    if (n == 0) return SDA_OK;
+    if (!shares || !out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    CU(ctx->in.reserve(n * sizeof(int64_t)));
+    CU(ctx->out.reserve(10 * n + 16));
+    OK(h2d(ctx, ctx->in.p, shares, n * sizeof(int64_t)));
+    size_t len = 0;
+    OK(sda_varint_encode_dev(ctx, (const int64_t *)ctx->in.p, n, (uint8_t *)ctx->out.p, &len));
+    if (out_len) *out_len = len;
+    return d2h(ctx, out, ctx->out.p, len);
+}
+
+int sda_varint_decode(sda_ctx *ctx, const uint8_t *buf, size_t len, int64_t *shares_out, size_t cap, size_t *n) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (n) *n = 0;
+    if (len == 0) return SDA_OK;
+    if (!buf || (!shares_out && cap)) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    CU(ctx->in.reserve(len + 16));
+    CU(ctx->out.reserve(std::max<size_t>(cap, 1) * sizeof(int64_t)));
+    OK(h2d(ctx, ctx->in.p, buf, len));
+    size_t cnt = 0;
+    OK(sda_varint_decode_dev(ctx, (const uint8_t *)ctx->in.p, len, (int64_t *)ctx->out.p, cap, &cnt));
+    if (n) *n = cnt;
+    return d2h(ctx, shares_out, ctx->out.p, cnt * sizeof(int64_t));
+}
+
 int sda_synth_fill_dev(sda_ctx *ctx, uint32_t stream, int64_t modulus, uint64_t start, size_t count, int64_t *d_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);

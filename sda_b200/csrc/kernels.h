@@ -110,6 +110,14 @@ void reveal_tc_build_image(int k, int m, const Matrix &R, uint8_t *img);
 cudaError_t launch_reveal_tc(const LaunchCtx &lc, int k, int m, const int64_t *shares, size_t ld, size_t dimension,
                              const uint8_t *d_b_image, int64_t *secrets_out);
 
+// ---- share wire codec (codec.cu): zig-zag LEB128 varints, encryption/sodium.rs:35-41,83-90 ----------
+// `scratch` holds *_scratch_elems u64; the encoded length / value count is left in scratch[elems - 1]
+size_t varint_encode_scratch_elems(size_t n);
+size_t varint_decode_scratch_elems(size_t len);
+cudaError_t launch_varint_encode(const LaunchCtx &lc, const int64_t *in, size_t n, uint8_t *out, uint64_t *scratch);
+cudaError_t launch_varint_decode(const LaunchCtx &lc, const uint8_t *buf, size_t len, int64_t *out, size_t cap,
+                                 uint64_t *scratch, unsigned *status);
+
 // ---- synthetic inputs ---------------------------------------------------------------------
 cudaError_t launch_synth_fill(const LaunchCtx &lc, const FieldParams &f, uint32_t stream_id, uint64_t start,
                               size_t count, int64_t *out);

@@ -125,6 +125,19 @@ def main():
         del rows, rec
         torch.cuda.empty_cache()
 
+        # ---- share wire codec: one clerk's share vector of config #3 (3.33M x 9 bytes) ------------------------
+        nsh = 3_333_334
+        shv = empty(nsh)
+        ctx.synth_fill_dev(8, P61, 0, nsh, shv)
+        enc = torch.empty(10 * nsh + 64, dtype=torch.uint8, device="cuda")
+        ln = ctx.varint_encode_dev(shv, nsh, enc)
+        dec = empty(nsh)
+        timeit("varint_encode [3.33M] 61-bit shares", lambda: ctx.varint_encode_dev(shv, nsh, enc), nsh, nsh * 8 + ln,
+               "read 8 B + write 9 B per share; includes the length read-back")
+        timeit("varint_decode [3.33M] 61-bit shares", lambda: ctx.varint_decode_dev(enc, ln, dec, nsh), nsh, nsh * 8 + ln)
+        del shv, enc, dec
+        torch.cuda.empty_cache()
+
         # ---- masks, dim = 25M (config #5's vector) --------------------------------------------------------
         dim = 25_000_000
         sec = empty(dim)
