@@ -406,6 +406,18 @@ __device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ 
     }
 }
 
+// the K secrets of batch b of participants p0 .. p0 + GP - 1 (zero beyond P and beyond the vector)
+template <class F, int K>
+__device__ __forceinline__ void load_secrets_fused(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t P,
+                                                   size_t p0, size_t e0, int64_t (&s)[F::GP][2 * F::S::SC]) {
+#pragma unroll
+    for (int q = 0; q < F::GP; q++) {
+        const int64_t *sec = secrets + (p0 + q) * ld;
+#pragma unroll
+        for (int i = 0; i < 2 * F::S::SC; i++) s[q][i] = (i < K && p0 + q < P && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+    }
+}
+
 template <int K, int T, int N, int ROUNDS>
 __global__ void __launch_bounds__(CTA)
 packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t P,
@@ -443,8 +455,12 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
 
     const size_t ranges = (B + CTA - 1) / CTA;
     const size_t groups = (P + F::GP - 1) / F::GP;
-    // keystream of the first pass
-    if (blockIdx.x < ranges && (size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+    // keystream and secrets of the first pass
+    int64_t s[F::GP][2 * S::SC];
+    if (blockIdx.x < ranges) {
+        load_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, s);
+        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+    }
 
     for (size_t r = blockIdx.x; r < ranges; r += gridDim.x) {
         const size_t b = r * CTA + tid;                    // this thread's batch
@@ -464,18 +480,14 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
 #pragma unroll
             for (int q = 0; q < F::GP; q++) {
                 if (q < np) {
-                    const int64_t *sec = secrets + (p0 + q) * ld;
-                    int64_t s[2 * S::SC];
-#pragma unroll
-                    for (int i = 0; i < 2 * S::SC; i++) s[i] = (i < K && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
 #pragma unroll
                     for (int i = 0; i < K; i++)
-                        if (s[i] < 0) s[i] = (int64_t)canon_negative(s[i]);
+                        if (s[q][i] < 0) s[q][i] = (int64_t)canon_negative(s[q][i]);
 #pragma unroll
                     for (int c = 0; c < S::SC; c++) {
                         uint32_t al, ah, bl, bh;
-                        unpack((uint64_t)s[2 * c], al, ah);
-                        unpack((uint64_t)s[2 * c + 1], bl, bh);
+                        unpack((uint64_t)s[q][2 * c], al, ah);
+                        unpack((uint64_t)s[q][2 * c + 1], bl, bh);
                         *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) =
                             make_uint4(al, ah, bl, bh);
                     }
@@ -502,12 +514,15 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
             in_tmem += np;
             // ---- the next pass's keystream (next participants of this range, or the next range) under the MMAs
             {
-                size_t rn = r, pn = p0 + F::GP + warp;
+                size_t rn = r, pg = p0 + F::GP;
                 if (g + 1 == groups) {
                     rn = r + gridDim.x;
-                    pn = warp;
+                    pg = 0;
                 }
-                if (rn < ranges && pn < P) stage_draws_fused<F, ROUNDS>(keys, pn, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
+                if (rn < ranges) {
+                    load_secrets_fused<F, K>(secrets, ld, dim, P, pg, (rn * CTA + tid) * K, s);     // consumed after the keystream
+                    if (pg + warp < P) stage_draws_fused<F, ROUNDS>(keys, pg + warp, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
+                }
             }
             mbar_wait(full_bar, parity);                   // rows consumed: the next pass may overwrite the secrets
             parity ^= 1;
