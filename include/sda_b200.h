@@ -25,6 +25,8 @@
  *   SecretUnmasker::unmask                         client/src/crypto/masking/mod.rs:29-31   sda_unmask
  *     (none.rs:28-33, full.rs:54-66, chacha.rs:79-92)
  *   RecipientOutput::positive                      client/src/receive.rs:13-21              (outputs are already canonical)
+ *   ShareEncryptor/Decryptor varint loops          client/src/crypto/encryption/sodium.rs   sda_varint_encode / _decode
+ *     (:35-41, :83-90; the sealed box itself stays with libsodium)
  *
  * Conventions
  *   - Element type is int64_t (`Secret/Mask/MaskedSecret/Share = i64`, client/src/crypto/mod.rs:33-36).
@@ -218,6 +220,15 @@ int sda_varint_decode(sda_ctx *ctx, const uint8_t *buf, size_t len, int64_t *sha
 /* device buffers; the length / count comes back through a host pointer (one stream synchronisation) */
 int sda_varint_encode_dev(sda_ctx *ctx, const int64_t *d_shares, size_t n, uint8_t *d_out, size_t *out_len);
 int sda_varint_decode_dev(sda_ctx *ctx, const uint8_t *d_buf, size_t len, int64_t *d_shares_out, size_t cap, size_t *n);
+
+/* ---- fixed-point codec for real-valued vectors (model updates) -------------------------------- */
+/* Not in the reference, whose API takes Vec<i64> (client/src/participate.rs:10,25): the adjacent step
+ * BASELINE config #5 needs.  encode: rint(x * 2^frac_bits) (ties to even) as a residue in [0, m);
+ * decode: centred lift in (-m/2, m/2], divided by 2^frac_bits and by `divisor` (e.g. the participant
+ * count, for a mean) in double, rounded to float.  frac_bits in [0, 52].  Device buffers. */
+int sda_fixed_encode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, const float *d_x, size_t n, int64_t *d_out);
+int sda_fixed_decode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, uint64_t divisor, const int64_t *d_in, size_t n,
+                         float *d_out);
 
 /* Synthetic benchmark / test inputs, generated on the device: out[i] = value(start + i) where
  * value(e) = u64 draw e of ChaCha20(key "sda-b200-synthetic-v1", key word 7 = stream) mod m.

@@ -252,6 +252,20 @@ def varint_decode(buf, max_out=None):
     return out[:n].copy()
 
 
+def fixed_encode(x, frac_bits, modulus):
+    v = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    out = np.empty(len(v), dtype=np.int64)
+    lib().sdao_fixed_encode(_p(v), C.c_size_t(len(v)), C.c_int(frac_bits), C.c_int64(modulus), _p(out))
+    return out
+
+
+def fixed_decode(values, frac_bits, modulus, divisor=1):
+    v = np.ascontiguousarray(np.asarray(values, dtype=np.int64))
+    out = np.empty(len(v), dtype=np.float32)
+    lib().sdao_fixed_decode(_p(v), C.c_size_t(len(v)), C.c_int(frac_bits), C.c_int64(modulus), C.c_uint64(divisor), _p(out))
+    return out
+
+
 def synth_fill(stream, modulus, start, count):
     out = np.empty(count, dtype=np.int64)
     lib().sdao_synth_fill(C.c_uint32(stream), C.c_int64(modulus), C.c_uint64(start), C.c_size_t(count), _p(out))

@@ -572,6 +572,32 @@ size_t sdao_varint_decode(const uint8_t *buf, size_t len, int64_t *out, size_t m
 }
 
 /* ======================================================================================
+ * fixed-point codec for real-valued vectors.  NOT in the
+ * reference, whose API takes Vec<i64> (client/src/participate.rs:10,25; motive README.md:12-13):
+ * an adjacent addition with this definition, shared with the CUDA side.
+ *   encode: q = rint(x * 2^frac_bits) (ties to even, exact in double), residue q mod p in [0, p)
+ *   decode: centred lift c in (-p/2, p/2], value (double)c / 2^frac_bits / divisor, rounded to float
+ * ====================================================================================== */
+#include <math.h>
+void sdao_fixed_encode(const float *x, size_t n, int frac_bits, int64_t p, int64_t *out) {
+    const double scale = ldexp(1.0, frac_bits);
+    for (size_t i = 0; i < n; i++) {
+        int64_t q = llrint((double)x[i] * scale);
+        int64_t r = q % p;
+        out[i] = r < 0 ? r + p : r;
+    }
+}
+void sdao_fixed_decode(const int64_t *in, size_t n, int frac_bits, int64_t p, uint64_t divisor, float *out) {
+    const double scale = ldexp(1.0, frac_bits);
+    for (size_t i = 0; i < n; i++) {
+        int64_t r = in[i] % p;
+        if (r < 0) r += p;
+        int64_t c = r > p / 2 ? r - p : r;
+        out[i] = (float)((double)c / scale / (double)divisor);
+    }
+}
+
+/* ======================================================================================
  * synthetic inputs (definition shared with the CUDA side; not from the reference)
  * ====================================================================================== */
 void sdao_synth_fill(uint32_t stream, int64_t modulus, uint64_t start, size_t count, int64_t *out) {

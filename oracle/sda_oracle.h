@@ -145,6 +145,10 @@ size_t sdao_varint_decode(const uint8_t *buf, size_t len, int64_t *out, size_t m
 /* ---- synthetic benchmark inputs (shared definition with the CUDA side) ------ */
 /* value(e) = next_u64 of ChaCha20(key = "sda-b200-synthetic-v1" zero padded, key word 7 =
  * stream) at draw index e, reduced  % modulus.  Fills out[0..count) for e = start.. */
+/* fixed-point codec of real-valued vectors (not in the reference) */
+void sdao_fixed_encode(const float *x, size_t n, int frac_bits, int64_t p, int64_t *out);
+void sdao_fixed_decode(const int64_t *in, size_t n, int frac_bits, int64_t p, uint64_t divisor, float *out);
+
 void sdao_synth_fill(uint32_t stream, int64_t modulus, uint64_t start, size_t count, int64_t *out);
 
 /* ---- parameter search helpers (orders / generators in Z_p^*) --------------------------- */

@@ -353,6 +353,13 @@ class Context:
         self.check(self._lib.sda_varint_decode_dev(self._h, _dev_ptr(d_buf), length, _dev_ptr(d_out), cap, C.byref(cnt)))
         return cnt.value
 
+    # -- fixed-point codec of real-valued vectors (not in the reference; BASELINE config #5) ---------
+    def fixed_encode_dev(self, modulus, frac_bits, d_x, n, d_out):
+        self.check(self._lib.sda_fixed_encode_dev(self._h, modulus, frac_bits, _dev_ptr(d_x), n, _dev_ptr(d_out)))
+
+    def fixed_decode_dev(self, modulus, frac_bits, divisor, d_in, n, d_out):
+        self.check(self._lib.sda_fixed_decode_dev(self._h, modulus, frac_bits, divisor, _dev_ptr(d_in), n, _dev_ptr(d_out)))
+
     def synth_fill_dev(self, stream_id, modulus, start, count, d_out):
         self.check(self._lib.sda_synth_fill_dev(self._h, stream_id, modulus, start, count, _dev_ptr(d_out)))
 

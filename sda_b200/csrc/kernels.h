@@ -118,6 +118,12 @@ cudaError_t launch_varint_encode(const LaunchCtx &lc, const int64_t *in, size_t 
 cudaError_t launch_varint_decode(const LaunchCtx &lc, const uint8_t *buf, size_t len, int64_t *out, size_t cap,
                                  uint64_t *scratch, unsigned *status);
 
+// ---- fixed-point codec of real-valued vectors (misc.cu; definition in include/sda_b200.h) ------------
+cudaError_t launch_fixed_encode(const LaunchCtx &lc, const FieldParams &f, int frac_bits, const float *x, size_t n,
+                                int64_t *out);
+cudaError_t launch_fixed_decode(const LaunchCtx &lc, const FieldParams &f, int frac_bits, uint64_t divisor,
+                                const int64_t *in, size_t n, float *out);
+
 // ---- synthetic inputs ---------------------------------------------------------------------
 cudaError_t launch_synth_fill(const LaunchCtx &lc, const FieldParams &f, uint32_t stream_id, uint64_t start,
                               size_t count, int64_t *out);

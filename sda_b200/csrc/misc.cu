@@ -8,6 +8,9 @@
 //                 secrets_b = R . shares_b for every batch b.
 //   draw_exact    rand 0.3 `Range::ind_sample` loop: the e-th sample is the
 //                 e-th ACCEPTED u64 of the stream -> count / scan / scatter over the keystream.
+#include <algorithm>
+#include <cmath>
+
 #include "kernels.h"
 #include "vecio.cuh"
 
@@ -47,6 +50,29 @@ packed_reconstruct_kernel(const int64_t *__restrict__ shares, size_t ld, size_t 
             }
         }
         out[o] = (int64_t)(M61 ? reduce128_m61(hi, lo) : reduce128_generic(f, hi, lo));
+    }
+}
+
+// ---- fixed-point codec of real-valued vectors (not in the reference) ---------
+// encode: q = rint(x 2^frac_bits) (ties to even, exact in double) -> residue in [0, m)
+template <bool M61>
+__global__ void __launch_bounds__(CTA)
+fixed_encode_kernel(const float *__restrict__ x, size_t n, double scale, int64_t *__restrict__ out, FieldParams f) {
+    size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * CTA;
+    for (; i < n; i += stride) out[i] = (int64_t)canon<M61>(f, __double2ll_rn((double)__ldg(x + i) * scale));
+}
+// decode: centred lift of the residue, / 2^frac_bits / divisor in double, rounded to float
+template <bool M61>
+__global__ void __launch_bounds__(CTA)
+fixed_decode_kernel(const int64_t *__restrict__ in, size_t n, double scale, double divisor, float *__restrict__ out,
+                    FieldParams f) {
+    size_t i = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * CTA;
+    for (; i < n; i += stride) {
+        const uint64_t r = canon<M61>(f, __ldg(in + i));
+        const int64_t c = r > f.m / 2 ? (int64_t)r - (int64_t)f.m : (int64_t)r;
+        out[i] = (float)__ddiv_rn(__ddiv_rn((double)c, scale), divisor);
     }
 }
 
@@ -199,6 +225,30 @@ cudaError_t launch_packed_reconstruct(const LaunchCtx &lc, const FieldParams &f,
     else
         packed_reconstruct_kernel<false><<<grid, CTA, 0, lc.stream>>>(shares, ld, nb, dimension, k, m, R, secrets_out,
                                                                       f, lazy_terms(f.m));
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_encode(const LaunchCtx &lc, const FieldParams &f, int frac_bits, const float *x, size_t n,
+                                int64_t *out) {
+    if (n == 0) return cudaSuccess;
+    size_t ctas = std::min<size_t>((n + CTA - 1) / CTA, (size_t)lc.sm_count * 32);
+    const double scale = ldexp(1.0, frac_bits);
+    if (f.kind == FIELD_MERSENNE61) fixed_encode_kernel<true><<<(unsigned)ctas, CTA, 0, lc.stream>>>(x, n, scale, out, f);
+    else fixed_encode_kernel<false><<<(unsigned)ctas, CTA, 0, lc.stream>>>(x, n, scale, out, f);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fixed_decode(const LaunchCtx &lc, const FieldParams &f, int frac_bits, uint64_t divisor,
+                                const int64_t *in, size_t n, float *out) {
+    if (n == 0) return cudaSuccess;
+    size_t ctas = std::min<size_t>((n + CTA - 1) / CTA, (size_t)lc.sm_count * 32);
+    const double scale = ldexp(1.0, frac_bits);
+    if (f.kind == FIELD_MERSENNE61)
+        fixed_decode_kernel<true><<<(unsigned)ctas, CTA, 0, lc.stream>>>(in, n, scale, (double)divisor, out, f);
+    else
+        fixed_decode_kernel<false><<<(unsigned)ctas, CTA, 0, lc.stream>>>(in, n, scale, (double)divisor, out, f);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }

@@ -1,0 +1,104 @@
+"""BASELINE config #5 in miniature, end to end on one GPU: float updates -> fixed point -> ChaCha mask ->
+packed Shamir k=3/t=4 with 8 clerks (one more than config #5's 7, so that a clerk may go missing) -> per-clerk
+sums (materialised AND fused) -> reveal from 7 of the 8 -> unmask -> mean as floats.  Every stage against the oracle; the two clerk-sum paths against each other."""
+import numpy as np
+import pytest
+
+import sda_b200
+from sda_b200 import LinearMaskingScheme as LMS
+from sda_b200 import params
+
+import util
+
+pytestmark = pytest.mark.gpu
+P61 = params.P61
+FRAC = 24
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = sda_b200.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import oracle as O
+    O.lib()
+    return O
+
+
+def test_fixed_point_codec_matches_oracle(ctx, oracle):
+    import torch as t
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.standard_normal(10_001).astype(np.float32),
+                        np.array([0.0, -0.0, 1.0, -1.0, 2.0 ** -25, 3 * 2.0 ** -25, -(2.0 ** -25), 1e4, -1e4, 2.0 ** -24],
+                                 dtype=np.float32)])
+    for m in (P61, params.P61_GENERIC, (1 << 40) + 15):
+        d_q = t.empty(len(x), dtype=t.int64, device="cuda")
+        ctx.fixed_encode_dev(m, FRAC, t.from_numpy(x).cuda(), len(x), d_q)
+        ctx.synchronize()
+        q = d_q.cpu().numpy()
+        assert np.array_equal(q, oracle.fixed_encode(x, FRAC, m))
+        for div in (1, 7, 8192):
+            d_y = t.empty(len(x), dtype=t.float32, device="cuda")
+            ctx.fixed_decode_dev(m, FRAC, div, d_q, len(x), d_y)
+            ctx.synchronize()
+            assert np.array_equal(d_y.cpu().numpy(), oracle.fixed_decode(q, FRAC, m, div))
+    back = oracle.fixed_decode(oracle.fixed_encode(x, FRAC, P61), FRAC, P61, 1)
+    assert np.max(np.abs(back - x)) <= 2.0 ** -25 * 1.0001 + 1e4 * 2.0 ** -24   # one rounding step (+ float ulp at 1e4)
+
+
+def test_federated_round_trip(ctx, oracle):
+    import torch as t
+    s = sda_b200.LinearSecretSharingScheme.PackedShamir(3, 8, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
+    n, k = s.output_size(), s.input_size()
+    P, dim = 37, 5000
+    B = s.batches(dim)
+    rng = np.random.default_rng(12)
+    updates = rng.standard_normal((P, dim)).astype(np.float32)
+    ms = LMS.ChaCha(P61, dim, 128)
+    mo = util.to_oracle_masking(oracle, ms)
+
+    # participants: encode, mask (mask seeds go to the recipient), share
+    d_x = t.from_numpy(updates).cuda()
+    d_q = t.empty((P, dim), dtype=t.int64, device="cuda")
+    ctx.fixed_encode_dev(P61, FRAC, d_x, P * dim, d_q)
+    ctx.synchronize()
+    q = d_q.cpu().numpy()
+    assert np.array_equal(q, oracle.fixed_encode(updates.ravel(), FRAC, P61).reshape(P, dim))
+    masked = np.empty_like(q)
+    seeds_for_recipient = []
+    for pi in range(P):
+        mask, masked[pi] = ctx.mask(ms, q[pi], util.seed_bytes(f"fed/mask/{pi}"))
+        emask, emasked = oracle.mask(mo, q[pi], oracle.rng_from_seed_bytes(util.seed_bytes(f"fed/mask/{pi}")))
+        assert mask.tolist() == emask.tolist() and np.array_equal(masked[pi], util.canon(oracle, P61, emasked))
+        seeds_for_recipient.append(mask)
+    share_seeds = b"".join(util.seed_bytes(f"fed/share/{pi}") for pi in range(P))
+    d_masked = t.from_numpy(masked).cuda()
+    d_shares = t.empty((P, n, B), dtype=t.int64, device="cuda")
+    ctx.share_generate_dev(s, d_masked, dim, P, dim, share_seeds, d_shares)
+
+    # clerks: per-clerk sums on the materialised shares, and the fused kernel that never materialises them
+    d_sums = t.empty((n, B), dtype=t.int64, device="cuda")
+    for c in range(n):
+        ctx.share_combine_dev(s, d_shares[:, c, :], n * B, P, B, d_sums[c])
+    d_fused = t.empty((n, B), dtype=t.int64, device="cuda")
+    ctx.share_generate_combine_dev(s, d_masked, dim, P, dim, share_seeds, d_fused)
+    ctx.synchronize()
+    assert t.equal(d_sums, d_fused)
+
+    # recipient: clerk 2 never answered; reveal from the other seven, combine the mask seeds, unmask, decode the mean
+    idx = [0, 1, 3, 4, 5, 6, 7]
+    got = ctx.secret_reconstruct(s, dim, [(i, d_sums[i].cpu().numpy()) for i in idx])
+    assert np.array_equal(got, masked.astype(object).sum(axis=0) % P61)
+    total_mask = ctx.mask_combine(ms, seeds_for_recipient)
+    summed = ctx.unmask(ms, total_mask, got)
+    assert np.array_equal(summed, q.astype(object).sum(axis=0) % P61)
+    d_mean = t.empty(dim, dtype=t.float32, device="cuda")
+    ctx.fixed_decode_dev(P61, FRAC, P, t.from_numpy(summed).cuda(), dim, d_mean)
+    ctx.synchronize()
+    mean = d_mean.cpu().numpy()
+    assert np.array_equal(mean, oracle.fixed_decode(summed, FRAC, P61, P))
+    assert np.max(np.abs(mean - updates.astype(np.float64).mean(axis=0))) < 2.0 ** -24
