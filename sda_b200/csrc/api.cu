@@ -399,11 +399,11 @@ int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
 // the constant GEMM operand of the tensor-core share-generation kernels, resident on the device per scheme
 int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
     const size_t ib = packed_share_tc_image_bytes(pk.k, pk.t, pk.n);
-    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n};
+    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
     key.insert(key.end(), M.e, M.e + M.rows * M.cols);
     if (key == ctx->tc_image_key) return SDA_OK;
     std::vector<uint8_t> img(ib);
-    packed_share_tc_build_image(pk.k, pk.t, pk.n, M, img.data());
+    packed_share_tc_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
     CU(ctx->tc_image.reserve(ib));
     CU(cudaMemcpyAsync(ctx->tc_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
@@ -440,13 +440,13 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     const ChaChaKey *d_keys = (const ChaChaKey *)ctx->keys.p;
     const bool fast = additive ? (n == 1 || additive_split_has_fast_path(n)) : packed_share_has_fast_path(pk.k, pk.t, pk.n);
     bool exact = !fast;
-    // Mersenne-61 fast shapes: tensor-core kernel unless the context asks for the CUDA-core one
-    const bool use_tc = !additive && fast && f.kind == FIELD_MERSENNE61 && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
+    // instantiated shapes, any prime: tensor-core kernel unless the context asks for the CUDA-core one
+    const bool use_tc = !additive && fast && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
                         packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0;
     if (use_tc) {
         OK(ensure_tc_image(ctx, pk, M));
         OK(clear_flags(ctx));
-        CU(launch_packed_share_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, d_keys,
+        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, d_keys,
                                   (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
         unsigned rejected = 0;
         OK(read_flags(ctx, &rejected, nullptr));

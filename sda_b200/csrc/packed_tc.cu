@@ -123,6 +123,35 @@ __device__ __forceinline__ uint64_t reduce_draw(uint32_t w0, uint32_t w1, uint32
     return pack(w1, hi) + (uint64_t)(2u * h);
 }
 
+// ---- any prime below 2^63 -----------------------------------------------------------------------------
+// The byte-limb GEMM does not care about the modulus (the constants are reduced on the host); only the two
+// scalar steps around it do: a draw is v mod (p - 1) by reciprocal multiplication with gen_range's rejection
+// zone tested exactly, and the limb sums are composed into a 79-bit integer and reduced once (field.cuh).
+struct GenericField {
+    FieldParams f;       // p
+    DrawParams dr;       // range p - 1
+};
+
+__device__ __forceinline__ uint64_t reduce_draw_generic(const DrawParams &dr, uint32_t w0, uint32_t w1, uint32_t &suspect) {
+    const uint64_t v = pack(w1, w0);
+    if (v >= dr.zone) suspect |= 1u << 29;                  // rejected by gen_range: the stream shifts, host redoes the call
+    return reduce64_generic(dr.f, v);
+}
+
+__device__ __forceinline__ uint64_t compose_generic(const uint32_t (&d)[8], uint32_t two16, const FieldParams &f) {
+    const uint32_t e0 = d[0] + (d[1] << 8), e1 = d[2] + (d[3] << 8);
+    const uint32_t e2 = d[4] + (d[5] << 8), e3 = d[6] + (d[7] << 8);
+    const uint64_t L = mac_u(e1, two16, e0), H = mac_u(e3, two16, e2);           // value = L + H 2^32 < 2^80
+    const uint64_t lo = L + (H << 32);
+    uint64_t hi = (H >> 32) + (lo < L);                                          // < 2^17
+    if (f.m <= (1ull << 17)) hi = reduce64_generic(f, hi);                       // reduce128 needs hi < m (uniform branch)
+    return reduce128_generic(f, hi, lo);
+}
+
+static __device__ __noinline__ uint64_t canon_negative_generic(const FieldParams &f, int64_t v) {
+    return canon<false>(f, v);
+}
+
 // one thread: the NK MMAs of a 128-row tile, completion signalled on `full_bar`
 template <class S>
 __device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_base, uint32_t full_bar) {
@@ -137,9 +166,9 @@ __device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint
 }
 
 // the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to
-template <class S, int ROUNDS>
+template <class S, int ROUNDS, bool M61>
 __device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, size_t p, size_t u, int tid, uint8_t *sD,
-                                            unsigned *flag) {
+                                            const GenericField &gf, unsigned *flag) {
     uint32_t k[8];
     const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
     const uint4 ka = __ldg(src), kb = __ldg(src + 1);
@@ -153,8 +182,10 @@ __device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, 
         uint32_t suspect = 0;
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {                          // 4 chunks of 2 draws
-            const uint64_t xa = reduce_draw(w[4 * cb], w[4 * cb + 1], suspect);
-            const uint64_t xb = reduce_draw(w[4 * cb + 2], w[4 * cb + 3], suspect);
+            const uint64_t xa = M61 ? reduce_draw(w[4 * cb], w[4 * cb + 1], suspect)
+                                    : reduce_draw_generic(gf.dr, w[4 * cb], w[4 * cb + 1], suspect);
+            const uint64_t xb = M61 ? reduce_draw(w[4 * cb + 2], w[4 * cb + 3], suspect)
+                                    : reduce_draw_generic(gf.dr, w[4 * cb + 2], w[4 * cb + 3], suspect);
             const uint32_t gc = slot * 4 + cb;                    // chunk index of the pass
             const uint32_t batch = gc / S::DC, c = gc % S::DC;
             const uint32_t q = batch / CTA, row = batch % CTA;
@@ -165,7 +196,7 @@ __device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, 
                 make_uint4(xal, xah, xbl, xbh);
         }
         if (suspect & (1u << 29)) {
-            bool bad = false;
+            bool bad = !M61;
 #pragma unroll
             for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;
             if (bad) atomicOr(flag, 1u);
@@ -197,11 +228,11 @@ __device__ __forceinline__ void load_secrets(const int64_t *__restrict__ secrets
     }
 }
 
-template <int K, int T, int N, int ROUNDS>
+template <int K, int T, int N, int ROUNDS, bool M61>
 __global__ void __launch_bounds__(CTA, SDA_TC_MINBLOCKS)
 packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t units_per_p,
                        size_t units_total, const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
-                       int64_t *__restrict__ out, uint32_t two16, unsigned *flag) {
+                       int64_t *__restrict__ out, uint32_t two16, const __grid_constant__ GenericField gf, unsigned *flag) {
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (G tiles x 128 rows x draws)
@@ -240,7 +271,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     int64_t s[S::G][2 * S::SC];                              // secrets of the coming pass, prefetched
     if (blockIdx.x < units_total) {
         load_secrets<S, K>(secrets, ld, dim, p, u, tid, s);
-        stage_draws<S, ROUNDS>(keys, p, u, tid, sD, flag);
+        stage_draws<S, ROUNDS, M61>(keys, p, u, tid, sD, gf, flag);
     }
 
     for (size_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
@@ -256,7 +287,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
                 if ((int32_t)sign < 0) {
 #pragma unroll
                     for (int i = 0; i < K; i++)
-                        if (s[q][i] < 0) s[q][i] = (int64_t)canon_negative(s[q][i]);
+                        if (s[q][i] < 0) s[q][i] = (int64_t)(M61 ? canon_negative(s[q][i]) : canon_negative_generic(gf.f, s[q][i]));
                 }
 #pragma unroll
                 for (int c = 0; c < S::SC; c++) {
@@ -283,7 +314,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
             pn++;
         }
         const bool more = unit + gridDim.x < units_total;
-        if (more) stage_draws<S, ROUNDS>(keys, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
+        if (more) stage_draws<S, ROUNDS, M61>(keys, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, gf, flag);
 #if SDA_TC_PREFETCH == 2
         if (more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
@@ -317,7 +348,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
             const bool live = b < B;
 #pragma unroll
             for (int j = 0; j < N; j++) {
-                const uint64_t r = compose(d[j], two16);
+                const uint64_t r = M61 ? compose(d[j], two16) : compose_generic(d[j], two16, gf.f);
                 if (live) *reinterpret_cast<int64_t *>(ob + (size_t)j * row_bytes) = (int64_t)r;
             }
         }
@@ -555,7 +586,7 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
 
 // the constant operand as it lies in shared memory
 template <int K, int T, int N>
-void build_b_image(const Matrix &m, uint8_t *img) {
+void build_b_image(const Matrix &m, uint64_t p, uint8_t *img) {
     typedef Shape<K, T, N> S;
     typedef unsigned __int128 u128;
     memset(img, 0, S::B_BYTES);
@@ -568,7 +599,7 @@ void build_b_image(const Matrix &m, uint8_t *img) {
                     const int xi = part ? idx : K + idx;        // index into x = [secrets ; randomness]
                     const int cg = part ? 2 * S::NKD + c : c;   // chunk along K of the whole row
                     for (int byte = 0; byte < 8; byte++) {
-                        const uint64_t cst = (uint64_t)((u128)m.e[j * (K + T) + xi] * ((((u128)1) << (8 * byte)) % P61) % P61);
+                        const uint64_t cst = (uint64_t)((u128)m.e[j * (K + T) + xi] * ((((u128)1) << (8 * byte)) % p) % p);
                         for (int s = 0; s < 8; s++) {
                             const int n = j * 8 + s;
                             img[(n / 8) * S::SBO_B + cg * LBO + (n % 8) * 16 + v * 8 + byte] = (uint8_t)(cst >> (8 * s));
@@ -577,15 +608,15 @@ void build_b_image(const Matrix &m, uint8_t *img) {
                 }
 }
 
-template <int K, int T, int N, int ROUNDS>
-cudaError_t launch(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                   const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
+template <int K, int T, int N, int ROUNDS, bool M61>
+cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *secrets, size_t ld, size_t P, size_t dim,
+                   const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
     typedef Shape<K, T, N> S;
     const size_t B = (dim + K - 1) / K;
     const size_t units_per_p = (B + S::G * CTA - 1) / (S::G * CTA);
     const size_t units_total = units_per_p * P;
     const size_t smem = S::SMEM;
-    auto kern = packed_share_tc_kernel<K, T, N, ROUNDS>;
+    auto kern = packed_share_tc_kernel<K, T, N, ROUNDS, M61>;
     static int per_sm = 0;      // resident CTAs per SM: every one of them must hold its TMEM columns
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -601,17 +632,24 @@ cudaError_t launch(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_
     size_t grid = (size_t)lc.sm_count * per_sm;
     if (grid > units_total) grid = units_total;
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, units_per_p, units_total, keys,
-                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, flag);
+                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, gf, flag);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
 
 template <int K, int T, int N>
-cudaError_t dispatch(const LaunchCtx &lc, int rounds, const int64_t *secrets, size_t ld, size_t P, size_t dim,
-                     const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
-    if (rounds == 8) return launch<K, T, N, 8>(lc, secrets, ld, P, dim, keys, d_b_image, out, flag);
-    if (rounds == 12) return launch<K, T, N, 12>(lc, secrets, ld, P, dim, keys, d_b_image, out, flag);
-    return launch<K, T, N, 20>(lc, secrets, ld, P, dim, keys, d_b_image, out, flag);
+cudaError_t dispatch(const LaunchCtx &lc, const GenericField &gf, int rounds, const int64_t *secrets, size_t ld, size_t P,
+                     size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
+#define SDA_L(R, M) return launch<K, T, N, R, M>(lc, gf, secrets, ld, P, dim, keys, d_b_image, out, flag)
+    if (gf.f.kind == FIELD_MERSENNE61) {
+        if (rounds == 8) SDA_L(8, true);
+        if (rounds == 12) SDA_L(12, true);
+        SDA_L(20, true);
+    }
+    if (rounds == 8) SDA_L(8, false);
+    if (rounds == 12) SDA_L(12, false);
+    SDA_L(20, false);
+#undef SDA_L
 }
 
 }  // namespace
@@ -659,20 +697,23 @@ size_t packed_share_tc_image_bytes(int k, int t, int n) {
     return 0;
 }
 
-void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint8_t *img) {
-#define X(K, T, N) if (k == K && t == T && n == N) return build_b_image<K, T, N>(mtx, img);
+void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img) {
+#define X(K, T, N) if (k == K && t == T && n == N) return build_b_image<K, T, N>(mtx, p, img);
     SDA_TC_SHAPES(X)
 #undef X
 }
 
 // d_b_image: device copy of the image built above (packed_share_tc_image_bytes bytes, 16-byte aligned)
-cudaError_t launch_packed_share_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
-                                   size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
-                                   int64_t *shares_out, unsigned *flag) {
-#define X(K, T, N)                                                                                        \
-    if (k == K && t == T && n == N) {                                                                     \
-        *lc.kernel_name = "packed_share<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8";           \
-        return dispatch<K, T, N>(lc, rounds, secrets, ld, P, dim, keys, d_b_image, shares_out, flag);     \
+cudaError_t launch_packed_share_tc(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k, int t,
+                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                                   const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag) {
+    const GenericField gf{f, dr};
+    const bool m61 = f.kind == FIELD_MERSENNE61;
+#define X(K, T, N)                                                                                              \
+    if (k == K && t == T && n == N) {                                                                           \
+        *lc.kernel_name = m61 ? "packed_share<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8"            \
+                              : "packed_share<" #K "," #T "," #N ">/any prime tcgen05.mma.kind::i8";            \
+        return dispatch<K, T, N>(lc, gf, rounds, secrets, ld, P, dim, keys, d_b_image, shares_out, flag);       \
     }
     SDA_TC_SHAPES(X)
 #undef X

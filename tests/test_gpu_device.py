@@ -130,6 +130,37 @@ def test_share_generate_combine_dev(ctx, oracle, torch_cuda):
         assert np.array_equal(host(out), exp)
 
 
+# a 61-bit prime not of Mersenne form; 2^31-1; the largest prime = 1 mod 2002 below 2^62 (the oracle's i64 sums limit
+# it to p < 2^62; the widest byte limbs it can check); and 1.3 * 2^61, for which gen_range rejects 2.5 % of the words,
+# so the kernel must notice and hand the call over to the exact path
+@pytest.mark.parametrize("p", [params.P61_GENERIC, (1 << 31) - 1, 4611686018427297811, 2997595911977817151],
+                         ids=["61bit", "mersenne31", "62bit", "61bit_rejecting"])
+# (3, 4, 8) is left to the reference's own parameters (tests/test_gpu_parity.py, p = 433): with k+t+1 = 2^3 and n+1 = 3^2
+# tss takes its FFT path, which is only defined for roots of exactly those orders
+@pytest.mark.parametrize("shape", [(3, 2, 5), (5, 4, 9), (3, 4, 7)], ids=["k3t2n5", "k5t4n9", "k3t4n7"])
+def test_packed_tensor_core_kernel_any_prime(ctx, oracle, torch_cuda, shape, p):
+    """the byte-limb GEMM kernel over primes that are not 2^61-1: generic draw reduction and compose"""
+    t = torch_cuda
+    k, tt, n = shape
+    try:
+        s = util.packed_scheme(p, k, tt, n, oracle)
+    except StopIteration:
+        pytest.skip("no suitable prime orders in p - 1")
+    rng = np.random.default_rng(31)
+    for P, dim in [(1, k), (2, 512 * k + 2), (3, 20000)]:
+        B = s.batches(dim)
+        secrets = rng.integers(0, p, size=(P, dim), dtype=np.int64)
+        secrets[0, ::5] = rng.integers(-(1 << 63), 1 << 63, size=secrets[0, ::5].shape, dtype=np.int64)
+        seeds = b"".join(util.seed_bytes(f"anyp/{p}/{shape}/{P}/{pi}") for pi in range(P))
+        d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_dev(s, dev(t, secrets), dim, P, dim, seeds, d_out)
+        ctx.synchronize()
+        got = host(d_out)
+        for pi in range(P):
+            exp = util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)
+            assert np.array_equal(got[pi], util.canon(oracle, p, exp)), (p, shape, P, dim, pi)
+
+
 @pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
 def test_fused_share_generate_combine_tmem_accumulation(ctx, oracle, torch_cuda, mk):
     """the fused tensor-core kernel sums the participants inside TMEM (drained every 256): participant counts

@@ -113,6 +113,26 @@ def main():
             del sec, sh
             torch.cuda.empty_cache()
 
+        # ---- the same shape over a 61-bit prime that is not of Mersenne form (generic reduction path) ----------
+        try:
+            from oracle import oracle as O          # only to find roots of unity for the other prime
+            pg = params.P61_GENERIC
+            qs = [q for q in range(7, 200) if (pg - 1) % q == 0 and all(q % d for d in range(2, q))]
+            sg = params.LinearSecretSharingScheme.PackedShamir(3, 5, 2, pg, O.find_root_of_order(pg, qs[0]),
+                                                               O.find_root_of_order(pg, qs[1]))
+            P, dim = 64, 10_000_000
+            n, B = 5, sg.batches(dim)
+            sec = empty(P, dim)
+            ctx.synth_fill_dev(9, pg, 0, P * dim, sec)
+            sh = empty(P, n, B)
+            sd = seeds("gen", P)
+            timeit(f"packed_share k=3 n=5 t=2 [{P}][10M], non-Mersenne 61-bit prime",
+                   lambda: ctx.share_generate_dev(sg, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n * B) * 8)
+            del sec, sh
+            torch.cuda.empty_cache()
+        except Exception as e:                       # no suitable orders: skip the line
+            print(json.dumps({"kernel": "packed_share generic prime", "skipped": str(e)}), flush=True)
+
         # ---- reveal with a missing clerk: the reference's own test shape over the 61-bit prime --------------
         s = params.LinearSecretSharingScheme.PackedShamir(3, 8, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
         dim = 10_000_000
