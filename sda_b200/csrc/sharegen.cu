@@ -62,20 +62,52 @@ additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim
     int64_t sh[D + 1][G];
     uint64_t blk[8];
     bool rej = false;
+    if constexpr (M61) {
+        // Mersenne path with as few ALU-pipe instructions as the arithmetic allows (the kernel is bound by
+        // ChaCha on that pipe, profiles/r01_pipes.md): a draw is (v & p) + (v >> 61) with NO compare -- that is
+        // gen_range's v % p unless the low 61 bits are within 8 of 2^61, which is detected through a carry into
+        // bit 29 of (hi + 1) and settled exactly in a rare branch -- and the last share is reduced once from
+        // x + D p - sum s_j instead of by D conditional subtractions (additive.rs:47, same residue).
+        constexpr uint32_t LOW29 = 0x1fffffffu;
 #pragma unroll
-    for (int e = 0; e < G; e++) {
-        uint64_t acc = canon<M61>(f, x[e]);
+        for (int e = 0; e < G; e++) {
+            uint64_t xe = (uint64_t)x[e];
+            if (xe >> 61) xe = canon<true>(f, x[e]);          // any i64 is a legal secret; [0, 2^61) needs no work
+            uint64_t t = xe + (uint64_t)D * P61;              // < 2^61 + 4 p
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-            const int q = e * D + j;
-            if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
-            bool r;
-            const uint64_t s = draw_reduce<DK>(dr, blk[q % 8], r);
-            rej |= r && e < nvalid;
-            sh[j][e] = (int64_t)s;                      // additive.rs:42-44
-            acc = submod(acc, s, f.m);                  // additive.rs:47
+            for (int j = 0; j < D; j++) {
+                const int q = e * D + j;
+                if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
+                const uint64_t v = blk[q % 8];
+                const uint32_t w0 = (uint32_t)(v >> 32), hi = w0 & LOW29;
+                uint64_t s = (((uint64_t)hi << 32) | (uint32_t)v) + (w0 >> 29);
+                if ((hi + 1u) >> 29) {                        // bits 32..60 all ones: 2^-29 per draw
+                    if (v >= dr.zone) rej |= e < nvalid;      // a word gen_range rejects: the stream shifts
+                    if (s >= P61) s -= P61;
+                }
+                sh[j][e] = (int64_t)s;                        // additive.rs:42-44
+                t -= s;
+            }
+            uint64_t r = (t & P61) + (t >> 61);               // <= p + 4
+            r = r >= P61 ? r - P61 : r;
+            sh[D][e] = (int64_t)r;
         }
-        sh[D][e] = (int64_t)acc;
+    } else {
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            uint64_t acc = canon<M61>(f, x[e]);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                const int q = e * D + j;
+                if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
+                bool r;
+                const uint64_t s = draw_reduce<DK>(dr, blk[q % 8], r);
+                rej |= r && e < nvalid;
+                sh[j][e] = (int64_t)s;                      // additive.rs:42-44
+                acc = submod(acc, s, f.m);                  // additive.rs:47
+            }
+            sh[D][e] = (int64_t)acc;
+        }
     }
     int64_t *o = out + (p * (D + 1)) * dim + e0;
 #pragma unroll
