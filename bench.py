@@ -131,7 +131,10 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi polled every 25 ms from before the warm-up; stop(t0, t1) keeps the samples whose timestamps
+    fall inside the timed region [t0, t1] (wall clock), falling back to every sample taken under load
+    (warm-up + timed steps run the same kernels back to back) when the region is too short to hold two."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -140,11 +143,12 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
@@ -155,28 +159,32 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
+        rows = []
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 9:
+            if len(parts) < 10:
                 continue
             try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-                power.append(float(parts[3]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]),
+                             [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                                parts[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         self.f.close()
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=max(power))
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        window = "timed region"
+        if len(inside) < 2:          # a ~100 ms region holds few 25 ms samples: use everything under load since warm-up
+            inside = [r for r in rows if r[0] <= t1 and r[3] > 0.5 * max(x[3] for x in rows)] if rows else []
+            window = "warm-up + timed region (samples drawing > half of the maximum power)"
+        if inside:
+            out.update(sm_mhz=statistics.median(r[1] for r in inside), sm_max_mhz=max(r[2] for r in inside),
+                       reasons=sorted({n for r in inside for n in r[4]}), samples=len(inside),
+                       power_w_max=max(r[3] for r in inside), window=window)
         return out
 
 
@@ -260,24 +268,26 @@ def run_ours(args):
                 return a, b, c
             return None
 
+        sampler = ClockSampler(local) if rank == 0 else None
         for w in range(args.warmup):
             step(-1 - w, False)
         ctx.synchronize()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
         launches0 = ctx.launch_count()
         t_start, t_end = ev(), ev()
         torch.cuda.synchronize()
+        wall0 = time.time()
         t_start.record(stream)
         marks = [step(i, True) for i in range(args.steps)]
         t_end.record(stream)
         ctx.synchronize()
         torch.cuda.synchronize()
+        wall1 = time.time()
         if world > 1:
             dist.barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(wall0, wall1) if sampler else None
         launches = ctx.launch_count() - launches0
         total_ms = t_start.elapsed_time(t_end)
         for a, b, c in marks:

@@ -63,7 +63,8 @@ def main():
         line = {"kernel": name, "ms_best": best, "ms_median": med, "elements": elements,
                 "elements_per_s": elements / (med * 1e-3), "algorithmic_bytes": alg_bytes,
                 "GBps": alg_bytes / (med * 1e-3) / 1e9, "frac_of_hbm_peak": alg_bytes / (med * 1e-3) / 1e9 / peak,
-                "peak_GBps": peak, "variant": ctx.last_kernel(), "rng_rounds": args.rounds, "note": note}
+                "peak_GBps": peak, "variant": ctx.last_kernel() if name.startswith(("additive_split", "packed_share")) else "",
+                "rng_rounds": args.rounds, "note": note}
         print(json.dumps(line), flush=True)
 
     def empty(*shape):
