@@ -84,6 +84,8 @@ struct sda_ctx {
     std::vector<uint64_t> tc_image_r_key; // (k, m', R) likewise for the reconstruction operand
     std::vector<uint64_t> r_key;          // (scheme, clerk subset) of r_cached
     Matrix r_cached;
+    std::vector<uint64_t> m_key;          // (scheme, evaluation points) of m_cached
+    Matrix m_cached;
     unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
     unsigned *h_flag = nullptr;    // pinned mirror
     PinBuf stage[2];               // pinned staging for pageable host buffers
@@ -238,6 +240,9 @@ int share_matrix(sda_ctx *ctx, const Packed &pk, Matrix *M) {
     return SDA_OK;
 }
 
+// the share matrix of the scheme the context used last (a participant shares many vectors under one scheme)
+int share_matrix_cached(sda_ctx *ctx, const Packed &pk, Matrix *M);
+
 // R[e][s] = lambda_{s+1}(a_{e+1}) over nodes {1} u {b_{idx_s}}; node-1 column dropped
 int reconstruct_matrix(sda_ctx *ctx, const Packed &pk, const uint64_t *indices, size_t m, Matrix *R) {
     if (m > (size_t)MAX_N) return fail(ctx, SDA_ERR_UNSUPPORTED, "more than %d indexed shares", MAX_N);
@@ -257,6 +262,18 @@ int reconstruct_matrix(sda_ctx *ctx, const Packed &pk, const uint64_t *indices, 
         for (size_t s = 0; s < m; s++)
             if (!lagrange_h(z, s + 1, pk.a[e + 1], pk.p, &R->e[e * m + s]))
                 return fail(ctx, SDA_ERR_INVALID, "prime_modulus is not prime (non-invertible difference of points)");
+    return SDA_OK;
+}
+
+int share_matrix_cached(sda_ctx *ctx, const Packed &pk, Matrix *M) {
+    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
+    key.insert(key.end(), pk.a.begin(), pk.a.end());
+    key.insert(key.end(), pk.b.begin(), pk.b.end());
+    if (key != ctx->m_key) {
+        OK(share_matrix(ctx, pk, &ctx->m_cached));
+        ctx->m_key = key;
+    }
+    *M = ctx->m_cached;
     return SDA_OK;
 }
 
@@ -432,7 +449,7 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     } else {
         if (s->modulus < 3) return fail(ctx, SDA_ERR_INVALID, "prime_modulus too small");
         dr = make_draw((uint64_t)s->modulus - 1);   // tss share(): Range::new(0, prime - 1)
-        OK(share_matrix(ctx, pk, &M));
+        OK(share_matrix_cached(ctx, pk, &M));
         B = (dim + pk.k - 1) / pk.k;
         dpe = (size_t)pk.t;
     }
@@ -837,7 +854,7 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
         if (packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
             if (!seeds) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
             Matrix M;
-            OK(share_matrix(ctx, pk, &M));
+            OK(share_matrix_cached(ctx, pk, &M));
             OK(ensure_tc_image(ctx, pk, M));
             OK(upload_keys(ctx, seeds, P));
             OK(clear_flags(ctx));
