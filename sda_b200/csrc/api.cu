@@ -72,7 +72,8 @@ struct sda_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // copy engines of the sliced host entry points
+    std::vector<cudaEvent_t> pipe_ev;                          // their per-slice events, grown on demand
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int rounds = 20;
     uint64_t nlaunch = 0;
@@ -413,6 +414,31 @@ int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
     return SDA_OK;
 }
 
+// ---- sliced host entry points: H2D of slice i+1, the kernel of slice i and D2H of slice i-1 run concurrently
+// on the two copy engines and the SMs (pinned host buffers only; PCIe is full duplex) ------------------------
+constexpr size_t PIPE_MIN_BYTES = 4u << 20;    // below this a call is latency-bound and stays on one stream
+constexpr size_t PIPE_SLICES = 8;
+
+int pipe_event(sda_ctx *ctx, size_t i, cudaEvent_t *out) {
+    while (ctx->pipe_ev.size() <= i) {
+        cudaEvent_t e;
+        CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_ev.push_back(e);
+    }
+    *out = ctx->pipe_ev[i];
+    return SDA_OK;
+}
+
+// the copy streams start after everything already queued on the compute stream (earlier calls reuse ctx->in / out)
+int pipe_begin(sda_ctx *ctx) {
+    cudaEvent_t e;
+    OK(pipe_event(ctx, 0, &e));
+    CU(cudaEventRecord(e, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->h2d_stream, e, 0));
+    CU(cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+    return SDA_OK;
+}
+
 // the constant GEMM operand of the tensor-core share-generation kernels, resident on the device per scheme
 int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
     const size_t ib = packed_share_tc_image_bytes(pk.k, pk.t, pk.n);
@@ -463,7 +489,7 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     if (use_tc) {
         OK(ensure_tc_image(ctx, pk, M));
         OK(clear_flags(ctx));
-        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, d_keys,
+        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, 0, B, d_keys,
                                   (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
         unsigned rejected = 0;
         OK(read_flags(ctx, &rejected, nullptr));
@@ -688,6 +714,8 @@ int sda_ctx_create(int device, sda_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     ctx = c;
     cudaError_t err = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking);
     if (err == cudaSuccess) err = cudaMalloc((void **)&c->d_flag, 2 * sizeof(unsigned));
     if (err == cudaSuccess) err = cudaMallocHost((void **)&c->h_flag, 2 * sizeof(unsigned));
     for (int i = 0; i < 4 && err == cudaSuccess; i++) err = cudaEventCreateWithFlags(&c->ev[i], cudaEventDisableTiming);
@@ -712,6 +740,9 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+    if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1054,6 +1085,56 @@ int sda_synth_fill_dev(sda_ctx *ctx, uint32_t stream, int64_t modulus, uint64_t 
 
 // ---- host-pointer entry points ---------------------------------------------------------------------
 
+// One participant's packed-Shamir shares with the vector walked in slices of batches: slice i is generated while
+// slice i + 1 is on its way in and slice i - 1 on its way out.  Taken for the tensor-core shapes with pinned
+// host buffers; *done stays false when the call should run the plain copy / kernel / copy sequence instead
+// (other schemes, pageable memory, short vectors, or a gen_range rejection, whose exact path reshuffles the
+// whole keystream).  ctx->in (ldp elements) and ctx->out (n B elements) are reserved by the caller.
+static int share_generate_sliced(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *secrets, size_t dim, size_t ldp,
+                                 const uint8_t *seed, int64_t *shares_out, bool *done) {
+    *done = false;
+    Packed pk;
+    OK(validate(ctx, s, &pk));
+    if (s->kind != SDA_SHARING_PACKED_SHAMIR || ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES || s->modulus < 3 || !seed)
+        return SDA_OK;
+    const size_t slice_unit = packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
+    if (slice_unit == 0 || dim * sizeof(int64_t) < PIPE_MIN_BYTES || !is_pinned(secrets) || !is_pinned(shares_out)) return SDA_OK;
+    const size_t n = (size_t)pk.n, k = (size_t)pk.k, B = (dim + k - 1) / k;
+    const size_t per = ((B + PIPE_SLICES - 1) / PIPE_SLICES + slice_unit - 1) / slice_unit * slice_unit;
+    const FieldParams f = make_field((uint64_t)s->modulus);
+    const DrawParams dr = make_draw((uint64_t)s->modulus - 1);
+    Matrix M;
+    OK(share_matrix_cached(ctx, pk, &M));
+    OK(ensure_tc_image(ctx, pk, M));
+    OK(upload_keys(ctx, seed, 1));
+    OK(clear_flags(ctx));
+    OK(pipe_begin(ctx));
+    const int64_t *d_in = (const int64_t *)ctx->in.p;
+    int64_t *d_out = (int64_t *)ctx->out.p;
+    size_t ei = 1;
+    for (size_t b0 = 0; b0 < B; b0 += per) {
+        const size_t nb = std::min(per, B - b0);
+        const size_t e0 = b0 * k, e1 = std::min(dim, (b0 + nb) * k);
+        cudaEvent_t in_ready, out_ready;
+        OK(pipe_event(ctx, ei++, &in_ready));
+        OK(pipe_event(ctx, ei++, &out_ready));
+        CU(cudaMemcpyAsync((void *)(d_in + e0), secrets + e0, (e1 - e0) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->h2d_stream));
+        CU(cudaEventRecord(in_ready, ctx->h2d_stream));
+        CU(cudaStreamWaitEvent(ctx->stream, in_ready, 0));
+        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_in, ldp, 1, dim, b0, nb,
+                                  (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
+        CU(cudaEventRecord(out_ready, ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->d2h_stream, out_ready, 0));
+        CU(cudaMemcpy2DAsync(shares_out + b0, B * sizeof(int64_t), d_out + b0, B * sizeof(int64_t), nb * sizeof(int64_t), n,
+                             cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    }
+    unsigned rejected = 0;
+    OK(read_flags(ctx, &rejected, nullptr));
+    CU(cudaStreamSynchronize(ctx->d2h_stream));
+    *done = rejected == 0;
+    return SDA_OK;
+}
+
 int sda_share_generate(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *secrets, size_t dim,
                        const uint8_t rng_seed[32], int64_t *shares_out) {
     if (!ctx) return SDA_ERR_INVALID;
@@ -1065,6 +1146,9 @@ int sda_share_generate(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t 
     const size_t ldp = (dim + 3) & ~(size_t)3;
     CU(ctx->in.reserve(ldp * sizeof(int64_t)));
     CU(ctx->out.reserve(n * B * sizeof(int64_t)));
+    bool done = false;
+    OK(share_generate_sliced(ctx, s, secrets, dim, ldp, rng_seed, shares_out, &done));
+    if (done) return SDA_OK;
     OK(h2d(ctx, ctx->in.p, secrets, dim * sizeof(int64_t)));
     OK(share_generate_core(ctx, s, (const int64_t *)ctx->in.p, ldp, 1, dim, rng_seed, (int64_t *)ctx->out.p));
     return d2h(ctx, shares_out, ctx->out.p, n * B * sizeof(int64_t));
@@ -1081,6 +1165,49 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
     CU(ctx->out.reserve(row_bytes));
     int64_t *d_in = (int64_t *)ctx->in.p, *d_acc = (int64_t *)ctx->out.p;
     if (P == 0) CU(cudaMemsetAsync(d_acc, 0, row_bytes, ctx->stream));
+    // pinned rows: walk the columns in slices so that the rows of slice i + 1 arrive while slice i is summed and
+    // the sums of slice i - 1 leave (the kernel takes any column range of the staged matrix: row stride ldp)
+    bool pinned = P > 0 && L * sizeof(int64_t) >= PIPE_MIN_BYTES && is_pinned(out);
+    if (pinned && shares) pinned = is_pinned(shares);
+    for (size_t p = 0; pinned && !shares && p < P; p++) pinned = is_pinned(rows[p]);
+    if (pinned) {
+        const size_t per = ((L + PIPE_SLICES - 1) / PIPE_SLICES + 1023) / 1024 * 1024;
+        const size_t se = combine_scratch_elems(ctx->sm_count, std::min(tile, P), std::min(per, L));
+        if (se) CU(ctx->scratch.reserve(se * sizeof(int64_t)));
+        OK(pipe_begin(ctx));
+        size_t ei = 1;
+        cudaEvent_t summed = nullptr;
+        for (size_t p0 = 0; p0 < P; p0 += tile) {
+            const size_t pc = std::min(tile, P - p0);
+            const bool last = p0 + pc == P;
+            if (summed) CU(cudaStreamWaitEvent(ctx->h2d_stream, summed, 0));   // the previous row tile is consumed
+            for (size_t c0 = 0; c0 < L; c0 += per) {
+                const size_t nc = std::min(per, L - c0);
+                cudaEvent_t in_ready;
+                OK(pipe_event(ctx, ei++, &in_ready));
+                OK(pipe_event(ctx, ei++, &summed));
+                if (shares) {
+                    CU(cudaMemcpy2DAsync(d_in + c0, row_bytes, shares + p0 * L + c0, L * sizeof(int64_t), nc * sizeof(int64_t), pc,
+                                         cudaMemcpyHostToDevice, ctx->h2d_stream));
+                } else {
+                    for (size_t p = 0; p < pc; p++)
+                        CU(cudaMemcpyAsync(d_in + p * ldp + c0, rows[p0 + p] + c0, nc * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                           ctx->h2d_stream));
+                }
+                CU(cudaEventRecord(in_ready, ctx->h2d_stream));
+                CU(cudaStreamWaitEvent(ctx->stream, in_ready, 0));
+                OK(combine_core(ctx, modulus, d_in + c0, ldp, pc, nc, p0 ? d_acc + c0 : nullptr, d_acc + c0));
+                CU(cudaEventRecord(summed, ctx->stream));
+                if (last) {
+                    CU(cudaStreamWaitEvent(ctx->d2h_stream, summed, 0));
+                    CU(cudaMemcpyAsync(out + c0, d_acc + c0, nc * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
+                }
+            }
+        }
+        CU(cudaStreamSynchronize(ctx->d2h_stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return SDA_OK;
+    }
     for (size_t p0 = 0; p0 < P; p0 += tile) {
         const size_t pc = std::min(tile, P - p0);
         if (shares && ldp == L) {

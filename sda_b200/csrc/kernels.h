@@ -86,10 +86,14 @@ cudaError_t launch_packed_share_m61(const LaunchCtx &lc, int rounds, int k, int 
 // passed as a 16-byte aligned device copy.
 size_t packed_share_tc_image_bytes(int k, int t, int n);
 void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img);
-// any prime below 2^63 (f = the field, dr = gen_range over [0, p - 1)); 2^61 - 1 takes the shift-and-add path
+// any prime below 2^63 (f = the field, dr = gen_range over [0, p - 1)); 2^61 - 1 takes the shift-and-add path.
+// Generates batches first_batch .. first_batch + n_batches - 1 (clipped to the vector) of every participant;
+// first_batch is a multiple of packed_share_tc_slice_batches(k, t, n); pointers address whole vectors.
+size_t packed_share_tc_slice_batches(int k, int t, int n);
 cudaError_t launch_packed_share_tc(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k, int t,
-                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                                   const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
+                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
+                                   size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *shares_out,
+                                   unsigned *flag);
 // fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,

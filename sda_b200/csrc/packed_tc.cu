@@ -44,6 +44,9 @@ using namespace tc;
 #define SDA_TC_PREFETCH 2   // where the next pass's secrets are loaded: 1 under the last tile's compose, 2 before the tile loop
 #endif
 
+#ifndef SDA_TC_ACC_BUFS
+#define SDA_TC_ACC_BUFS 1   // 2: two TMEM accumulators (measured: 16.94 ms against 16.90 ms with one -- the kernel is bound by
+#endif                      //    instruction issue, not by waiting for the MMA; profiles/r01_k2_variants.md)
 #ifndef SDA_TC_MINBLOCKS
 #define SDA_TC_MINBLOCKS 1
 #endif
@@ -76,7 +79,11 @@ struct Shape {
     static constexpr uint32_t SBO_B = 2 * NK * 128;
     static constexpr uint32_t B_BYTES = NMMA / 8 * SBO_B;
     static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + B_BYTES;
-    static constexpr int TMEM_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : NMMA <= 128 ? 128 : 256;
+    static constexpr int ACC_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : NMMA <= 128 ? 128 : 256;
+    // optionally two TMEM accumulators (when that still leaves four CTAs per SM their columns): tile q + 2 is
+    // multiplied while tile q + 1 is composed, so nobody waits for an MMA
+    static constexpr int ACC_BUFS = (SDA_TC_ACC_BUFS >= 2 && 2 * ACC_COLS <= 128 && G >= 2) ? 2 : 1;
+    static constexpr int TMEM_COLS = ACC_BUFS * ACC_COLS;
     static constexpr uint32_t IDESC = idesc_u8(NMMA);
     static_assert(4 % DC == 0, "a keystream block covers whole rows");
     static_assert(D_BYTES % 128 == 0 && S_BYTES % 128 == 0, "operand buffers stay 128-byte aligned");
@@ -230,7 +237,7 @@ __device__ __forceinline__ void load_secrets(const int64_t *__restrict__ secrets
 
 template <int K, int T, int N, int ROUNDS, bool M61>
 __global__ void __launch_bounds__(CTA, SDA_TC_MINBLOCKS)
-packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t units_per_p,
+packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t unit_begin, size_t units_per_p,
                        size_t units_total, const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
                        int64_t *__restrict__ out, uint32_t two16, const __grid_constant__ GenericField gf, unsigned *flag) {
     typedef Shape<K, T, N> S;
@@ -238,7 +245,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     uint8_t *sD = smem;                                    // 2 x (G tiles x 128 rows x draws)
     uint8_t *sS = smem + 2 * S::D_BYTES;                   // G tiles x 128 rows x secrets
     uint8_t *sB = sS + S::S_BYTES;                         // the constant operand
-    __shared__ __align__(8) uint64_t mbar[2];              // [0] full (MMA done), [1] drained (TMEM read out)
+    __shared__ __align__(8) uint64_t mbar[4];              // [a] full (MMA into accumulator a done), [2 + a] drained (read out)
     __shared__ uint32_t tmem_base;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -250,8 +257,11 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "n"(CTA) : "memory");
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[a])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[2 + a])), "n"(CTA) : "memory");
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < S::B_BYTES / 16; i += CTA) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
@@ -261,13 +271,18 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base;
     const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
-    const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[1]);
+    const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[2]);   // + 8 a
     const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
     const size_t row_bytes = B * sizeof(int64_t);           // distance between the share rows of a participant
-    uint32_t parity = 0, buf = 0;
+    uint32_t phase = 0, buf = 0;                             // bit a: parity of the next phase of full[a] / drained[a]
 
     // (participant, pass) of this CTA's current unit and of its next one
-    size_t p = blockIdx.x / units_per_p, u = blockIdx.x % units_per_p;
+    // (32-bit division: a 64-bit one is a call, and a call anywhere in the kernel makes ptxas keep the global
+    // memory descriptor in a vector register and copy it to a uniform one at every load and store)
+    // a launch covers passes unit_begin .. unit_begin + units_per_p - 1 of every participant (the host entry point
+    // walks a vector in slices so that its copies overlap the kernel; device callers pass the whole vector)
+    const size_t unit_end = unit_begin + units_per_p;
+    size_t p = blockIdx.x / (uint32_t)units_per_p, u = unit_begin + blockIdx.x % (uint32_t)units_per_p;
     int64_t s[S::G][2 * S::SC];                              // secrets of the coming pass, prefetched
     if (blockIdx.x < units_total) {
         load_secrets<S, K>(secrets, ld, dim, p, u, tid, s);
@@ -305,11 +320,15 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_cur = d_base + buf * S::D_BYTES;
-        if (tid == 0) issue_tile<S>(taddr, d_cur, s_base, b_base, full_bar);
+        if (tid == 0) {
+#pragma unroll
+            for (int a = 0; a < S::ACC_BUFS; a++)
+                issue_tile<S>(taddr + a * S::ACC_COLS, d_cur + a * S::D_TILE, s_base + a * S::S_TILE, b_base, full_bar + 8 * a);
+        }
 
         // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
         size_t pn = p, un = u + gridDim.x;
-        while (un >= units_per_p) {
+        while (un >= unit_end) {
             un -= units_per_p;
             pn++;
         }
@@ -320,36 +339,49 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
 #endif
 
         // ---- per tile: D = A . B^T on the tensor core, then compose the shares ------------------
-        // `full` completes when a tile's MMAs have written TMEM; `drained` when all 128 threads have
-        // read their lane out of it, so thread 0 can launch the next tile's MMAs under everyone's
-        // (and its own) compose arithmetic instead of after a CTA-wide barrier.
+        // `full[a]` completes when a tile's MMAs have written accumulator a; `drained[a]` when all 128 threads
+        // have read their lane out of it.  With two accumulators thread 0 launches tile q + 2 after its own
+        // compose of tile q (by then the others have drained it too, so it does not spin) and the MMAs run
+        // under the compose of tile q + 1; with one, tile q + 1 is launched as soon as tile q is drained.
+        // this thread's column of the share rows: batch b_first + q * CTA of tile q, live while it is below B
+        const size_t b_first = b_base_batch + tid;
+        char *ob = reinterpret_cast<char *>(out + p * (size_t)N * B + b_first);
+        const size_t rows_left = b_first < B ? B - b_first : 0;
+        const uint32_t live_rows = rows_left < (size_t)(S::G * CTA) ? (uint32_t)rows_left : (uint32_t)(S::G * CTA);
 #pragma unroll 1
         for (int q = 0; q < S::G; q++) {
-            mbar_wait(full_bar, parity);
+            const uint32_t a = S::ACC_BUFS == 2 ? (uint32_t)(q & 1) : 0u;
+            const uint32_t par = (phase >> a) & 1u;
+            phase ^= 1u << a;
+            mbar_wait(full_bar + 8 * a, par);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t d[N][8];
 #pragma unroll
-            for (int j = 0; j < N; j++) tmem_ld8(my_taddr + 8 * j, d[j]);
+            for (int j = 0; j < N; j++) tmem_ld8(my_taddr + a * S::ACC_COLS + 8 * j, d[j]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar + 8 * a) : "memory");
 #if SDA_TC_PREFETCH == 1
             // next pass's secrets: issued under the last tile's compose arithmetic, consumed after it
             if (q == S::G - 1 && more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
-            if (tid == 0 && q + 1 < S::G) {
-                mbar_wait(drained_bar, parity);
+            if (S::ACC_BUFS == 1 && tid == 0 && q + 1 < S::G) {
+                mbar_wait(drained_bar, par);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 issue_tile<S>(taddr, d_cur + (q + 1) * S::D_TILE, s_base + (q + 1) * S::S_TILE, b_base, full_bar);
             }
-            parity ^= 1;
-            const size_t b = b_base_batch + (size_t)q * CTA + tid;
-            char *ob = reinterpret_cast<char *>(out + p * (size_t)N * B + b);
-            const bool live = b < B;
+            const bool live = (uint32_t)(q * CTA) < live_rows;
 #pragma unroll
             for (int j = 0; j < N; j++) {
                 const uint64_t r = M61 ? compose(d[j], two16) : compose_generic(d[j], two16, gf.f);
                 if (live) *reinterpret_cast<int64_t *>(ob + (size_t)j * row_bytes) = (int64_t)r;
+            }
+            ob += CTA * sizeof(int64_t);
+            if (S::ACC_BUFS == 2 && tid == 0 && q + 2 < S::G) {
+                mbar_wait(drained_bar + 8 * a, par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                issue_tile<S>(taddr + a * S::ACC_COLS, d_cur + (q + 2) * S::D_TILE, s_base + (q + 2) * S::S_TILE, b_base,
+                              full_bar + 8 * a);
             }
         }
         // every thread is past its TMEM loads of the last tile and every MMA of this pass has completed
@@ -610,12 +642,22 @@ void build_b_image(const Matrix &m, uint64_t p, uint8_t *img) {
 
 template <int K, int T, int N, int ROUNDS, bool M61>
 cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *secrets, size_t ld, size_t P, size_t dim,
-                   const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
+                   size_t first_batch, size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out,
+                   unsigned *flag) {
     typedef Shape<K, T, N> S;
     const size_t B = (dim + K - 1) / K;
-    const size_t units_per_p = (B + S::G * CTA - 1) / (S::G * CTA);
+    if (first_batch % (S::G * CTA) != 0 || first_batch > B) return cudaErrorInvalidValue;
+    if (n_batches > B - first_batch) n_batches = B - first_batch;
+    const size_t unit_begin = first_batch / (S::G * CTA);
+    const size_t units_per_p = (n_batches + S::G * CTA - 1) / (S::G * CTA);
     const size_t units_total = units_per_p * P;
-    const size_t smem = S::SMEM;
+    if (units_total == 0) return cudaSuccess;
+    if (units_per_p >> 32) return cudaErrorInvalidValue;
+    size_t smem = S::SMEM;
+    // The block scheduler places CTAs by registers and shared memory only: where TMEM columns are the scarcest
+    // resource, a CTA too many would sit in tcgen05.alloc until a neighbour exits.  Ask for enough shared
+    // memory that exactly 512 / TMEM_COLS CTAs fit an SM.
+    if (512 / S::TMEM_COLS < 8) smem = std::max(smem, (size_t)(227u * 1024u) / (512 / S::TMEM_COLS + 1) + 1);
     auto kern = packed_share_tc_kernel<K, T, N, ROUNDS, M61>;
     static int per_sm = 0;      // resident CTAs per SM: every one of them must hold its TMEM columns
     if (per_sm == 0) {
@@ -631,7 +673,7 @@ cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *s
     }
     size_t grid = (size_t)lc.sm_count * per_sm;
     if (grid > units_total) grid = units_total;
-    kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, units_per_p, units_total, keys,
+    kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, unit_begin, units_per_p, units_total, keys,
                                                    reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, gf, flag);
     ++*lc.nlaunch;
     return cudaGetLastError();
@@ -639,8 +681,9 @@ cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *s
 
 template <int K, int T, int N>
 cudaError_t dispatch(const LaunchCtx &lc, const GenericField &gf, int rounds, const int64_t *secrets, size_t ld, size_t P,
-                     size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
-#define SDA_L(R, M) return launch<K, T, N, R, M>(lc, gf, secrets, ld, P, dim, keys, d_b_image, out, flag)
+                     size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image,
+                     int64_t *out, unsigned *flag) {
+#define SDA_L(R, M) return launch<K, T, N, R, M>(lc, gf, secrets, ld, P, dim, first_batch, n_batches, keys, d_b_image, out, flag)
     if (gf.f.kind == FIELD_MERSENNE61) {
         if (rounds == 8) SDA_L(8, true);
         if (rounds == 12) SDA_L(12, true);
@@ -703,17 +746,30 @@ void packed_share_tc_build_image(int k, int t, int n, const Matrix &mtx, uint64_
 #undef X
 }
 
-// d_b_image: device copy of the image built above (packed_share_tc_image_bytes bytes, 16-byte aligned)
+// batches one CTA pass covers: slices of a vector handed to launch_packed_share_tc start at multiples of it
+size_t packed_share_tc_slice_batches(int k, int t, int n) {
+#define X(K, T, N) if (k == K && t == T && n == N) return (size_t)Shape<K, T, N>::G * CTA;
+    SDA_TC_SHAPES(X)
+#undef X
+    return 0;
+}
+
+// d_b_image: device copy of the image built above (packed_share_tc_image_bytes bytes, 16-byte aligned).
+// Batches first_batch .. first_batch + n_batches - 1 of every participant are generated (n_batches is clipped to
+// the vector; first_batch is a multiple of packed_share_tc_slice_batches); `secrets` and `shares_out` always
+// address whole vectors.
 cudaError_t launch_packed_share_tc(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k, int t,
-                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                                   const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag) {
+                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
+                                   size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *shares_out,
+                                   unsigned *flag) {
     const GenericField gf{f, dr};
     const bool m61 = f.kind == FIELD_MERSENNE61;
 #define X(K, T, N)                                                                                              \
     if (k == K && t == T && n == N) {                                                                           \
         *lc.kernel_name = m61 ? "packed_share<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8"            \
                               : "packed_share<" #K "," #T "," #N ">/any prime tcgen05.mma.kind::i8";            \
-        return dispatch<K, T, N>(lc, gf, rounds, secrets, ld, P, dim, keys, d_b_image, shares_out, flag);       \
+        return dispatch<K, T, N>(lc, gf, rounds, secrets, ld, P, dim, first_batch, n_batches, keys, d_b_image,  \
+                                 shares_out, flag);                                                             \
     }
     SDA_TC_SHAPES(X)
 #undef X

@@ -33,11 +33,17 @@ __device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t da, uint64_t db
         "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
         :: "r"(taddr), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// the retry loop lives inside the asm block: written as a C loop around try_wait, ptxas recomputes the
+// barrier's shared-window address (S2R SR_CgaCtaId, MOV, LEA) on every iteration of the spin
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok)
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "SDA_MBAR_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SDA_MBAR_DONE;\n\t"
+        "bra SDA_MBAR_WAIT;\n"
+        "SDA_MBAR_DONE:\n\t}"
+        :: "r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
