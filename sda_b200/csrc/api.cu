@@ -417,7 +417,8 @@ int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
 // ---- sliced host entry points: H2D of slice i+1, the kernel of slice i and D2H of slice i-1 run concurrently
 // on the two copy engines and the SMs (pinned host buffers only; PCIe is full duplex) ------------------------
 constexpr size_t PIPE_MIN_BYTES = 4u << 20;    // below this a call is latency-bound and stays on one stream
-constexpr size_t PIPE_SLICES = 8;
+constexpr size_t PIPE_MAX_PITCH = 1u << 30;    // rows of the 2-D copies stay far below cudaDeviceProp::memPitch
+constexpr size_t PIPE_SLICES = 16;
 
 int pipe_event(sda_ctx *ctx, size_t i, cudaEvent_t *out) {
     while (ctx->pipe_ev.size() <= i) {
@@ -1098,7 +1099,9 @@ static int share_generate_sliced(sda_ctx *ctx, const sda_sharing_scheme *s, cons
     if (s->kind != SDA_SHARING_PACKED_SHAMIR || ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES || s->modulus < 3 || !seed)
         return SDA_OK;
     const size_t slice_unit = packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
-    if (slice_unit == 0 || dim * sizeof(int64_t) < PIPE_MIN_BYTES || !is_pinned(secrets) || !is_pinned(shares_out)) return SDA_OK;
+    if (slice_unit == 0 || dim * sizeof(int64_t) < PIPE_MIN_BYTES || dim * sizeof(int64_t) > PIPE_MAX_PITCH ||
+        !is_pinned(secrets) || !is_pinned(shares_out))
+        return SDA_OK;
     const size_t n = (size_t)pk.n, k = (size_t)pk.k, B = (dim + k - 1) / k;
     const size_t per = ((B + PIPE_SLICES - 1) / PIPE_SLICES + slice_unit - 1) / slice_unit * slice_unit;
     const FieldParams f = make_field((uint64_t)s->modulus);
@@ -1167,7 +1170,7 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
     if (P == 0) CU(cudaMemsetAsync(d_acc, 0, row_bytes, ctx->stream));
     // pinned rows: walk the columns in slices so that the rows of slice i + 1 arrive while slice i is summed and
     // the sums of slice i - 1 leave (the kernel takes any column range of the staged matrix: row stride ldp)
-    bool pinned = P > 0 && L * sizeof(int64_t) >= PIPE_MIN_BYTES && is_pinned(out);
+    bool pinned = P > 0 && L * sizeof(int64_t) >= PIPE_MIN_BYTES && L * sizeof(int64_t) <= PIPE_MAX_PITCH && is_pinned(out);
     if (pinned && shares) pinned = is_pinned(shares);
     for (size_t p = 0; pinned && !shares && p < P; p++) pinned = is_pinned(rows[p]);
     if (pinned) {
@@ -1175,12 +1178,12 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
         const size_t se = combine_scratch_elems(ctx->sm_count, std::min(tile, P), std::min(per, L));
         if (se) CU(ctx->scratch.reserve(se * sizeof(int64_t)));
         OK(pipe_begin(ctx));
-        size_t ei = 1;
         cudaEvent_t summed = nullptr;
         for (size_t p0 = 0; p0 < P; p0 += tile) {
             const size_t pc = std::min(tile, P - p0);
             const bool last = p0 + pc == P;
             if (summed) CU(cudaStreamWaitEvent(ctx->h2d_stream, summed, 0));   // the previous row tile is consumed
+            size_t ei = 1;                                                     // (a wait keeps the record it was queued behind)
             for (size_t c0 = 0; c0 < L; c0 += per) {
                 const size_t nc = std::min(per, L - c0);
                 cudaEvent_t in_ready;

@@ -653,13 +653,10 @@ cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *s
     const size_t units_total = units_per_p * P;
     if (units_total == 0) return cudaSuccess;
     if (units_per_p >> 32) return cudaErrorInvalidValue;
-    size_t smem = S::SMEM;
-    // The block scheduler places CTAs by registers and shared memory only: where TMEM columns are the scarcest
-    // resource, a CTA too many would sit in tcgen05.alloc until a neighbour exits.  Ask for enough shared
-    // memory that exactly 512 / TMEM_COLS CTAs fit an SM.
-    if (512 / S::TMEM_COLS < 8) smem = std::max(smem, (size_t)(227u * 1024u) / (512 / S::TMEM_COLS + 1) + 1);
     auto kern = packed_share_tc_kernel<K, T, N, ROUNDS, M61>;
-    static int per_sm = 0;      // resident CTAs per SM: every one of them must hold its TMEM columns
+    // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh)
+    const size_t smem = smem_capping_residency(S::SMEM, 512 / S::TMEM_COLS);
+    static int per_sm = 0;      // resident CTAs per SM
     if (per_sm == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -703,7 +700,7 @@ cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld,
     typedef FusedShape<K, T, N> F;
     const size_t B = (dim + K - 1) / K;
     const size_t ranges = (B + CTA - 1) / CTA;
-    const size_t smem = F::SMEM;
+    const size_t smem = smem_capping_residency(F::SMEM, 512 / F::TMEM_COLS);
     auto kern = packed_share_combine_tc_kernel<K, T, N, ROUNDS>;
     static int per_sm = 0;
     if (per_sm == 0) {

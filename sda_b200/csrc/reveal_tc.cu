@@ -84,21 +84,48 @@ reveal_tc_kernel(const int64_t *__restrict__ shares, size_t ld, size_t nbatches,
     uint32_t parity = 0;
 
     const size_t tiles = (nbatches + CTA - 1) / CTA;
+    // this thread's row of the coming tile -- the m shares of its batch, two per 16-byte chunk (batched.rs:83-85).
+    // Where TMEM leaves room for at most 8 CTAs per SM the row is loaded a tile ahead, in flight under the MMA and the
+    // compose of the current tile (9 x [2M] shares: 90 -> 76 us); with 32 columns per CTA the 16 resident CTAs hide
+    // the loads better than the 9 that the prefetch registers would leave (7 x [3.33M]: 81 us against 103 us).
+    constexpr bool PREFETCH = TMEM_COLS >= 64;
+    constexpr int MAX_CHUNKS = 8;                      // m' <= 16
+    int64_t v[2 * MAX_CHUNKS];
+    auto load_row = [&](size_t tile) {
+        const size_t b = tile * CTA + tid;
+#pragma unroll
+        for (int c = 0; c < MAX_CHUNKS; c++) {
+            v[2 * c] = v[2 * c + 1] = 0;
+            if (c < chunks && b < nbatches) {
+                v[2 * c] = __ldg(shares + (size_t)(2 * c) * ld + b);
+                if (2 * c + 1 < m) v[2 * c + 1] = __ldg(shares + (size_t)(2 * c + 1) * ld + b);
+            }
+        }
+    };
+    if (PREFETCH && blockIdx.x < tiles) load_row(blockIdx.x);
     for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const size_t b = tile * CTA + tid;
-        // ---- this thread's row: the m shares of batch b, two per 16-byte chunk (batched.rs:83-85) ----
-        for (int c = 0; c < chunks; c++) {
-            int64_t v0 = 0, v1 = 0;
-            if (b < nbatches) {
-                v0 = __ldg(shares + (size_t)(2 * c) * ld + b);
-                if (2 * c + 1 < m) v1 = __ldg(shares + (size_t)(2 * c + 1) * ld + b);
-            }
+        auto stage_chunk = [&](int c, int64_t v0, int64_t v1) {
             if (v0 < 0) v0 = (int64_t)canon_negative(v0);
             if (v1 < 0) v1 = (int64_t)canon_negative(v1);
             uint32_t al, ah, bl, bh;
             unpack((uint64_t)v0, al, ah);
             unpack((uint64_t)v1, bl, bh);
             *reinterpret_cast<uint4 *>(my_row + c * LBO) = make_uint4(al, ah, bl, bh);
+        };
+        if constexpr (PREFETCH) {
+#pragma unroll
+            for (int c = 0; c < MAX_CHUNKS; c++)
+                if (c < chunks) stage_chunk(c, v[2 * c], v[2 * c + 1]);
+        } else {
+            for (int c = 0; c < chunks; c++) {
+                int64_t v0 = 0, v1 = 0;
+                if (b < nbatches) {
+                    v0 = __ldg(shares + (size_t)(2 * c) * ld + b);
+                    if (2 * c + 1 < m) v1 = __ldg(shares + (size_t)(2 * c + 1) * ld + b);
+                }
+                stage_chunk(c, v0, v1);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -110,6 +137,7 @@ reveal_tc_kernel(const int64_t *__restrict__ shares, size_t ld, size_t nbatches,
                 umma_i8(taddr, da + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), idesc, kk > 0);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
         }
+        if (PREFETCH && tile + gridDim.x < tiles) load_row(tile + gridDim.x);
         mbar_wait(bar, parity);
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -132,7 +160,9 @@ template <int TMEM_COLS>
 cudaError_t launch(const LaunchCtx &lc, const RevealShape &s, const int64_t *shares, size_t ld, size_t nbatches,
                    size_t dimension, const uint8_t *d_b_image, int64_t *out) {
     auto kern = reveal_tc_kernel<TMEM_COLS>;
-    const size_t smem = ((s.a_bytes + 127) & ~127u) + s.b_bytes;
+    // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh): this kernel needs few registers
+    // and little shared memory, so without the floor 12 CTAs land on an SM that has columns for 512 / TMEM_COLS
+    const size_t smem = smem_capping_residency(((s.a_bytes + 127) & ~127u) + s.b_bytes, 512 / TMEM_COLS);
     static size_t smem_set = 0;
     static int regs = 0;
     if (smem > smem_set) {

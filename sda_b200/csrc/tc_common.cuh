@@ -22,6 +22,16 @@ __host__ __device__ constexpr uint32_t idesc_u8(int n_mma) {
     return (2u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
+// The block scheduler places CTAs by registers, threads and shared memory only.  A CTA that lands on an SM whose 512
+// TMEM columns are taken sits in tcgen05.alloc until a neighbour EXITS -- with persistent CTAs that serialises
+// whole shares of the grid and leaves other SMs empty (profiles/r01_k2_variants.md).  Kernels whose residency is
+// bounded by TMEM therefore ask for at least this much dynamic shared memory: more than 1 / (max_ctas + 1) of an
+// SM's 228 KB, so that max_ctas + 1 CTAs can never be resident whatever the per-CTA overheads are.
+inline size_t smem_capping_residency(size_t dyn_smem, int max_ctas) {
+    const size_t floor_bytes = (228u * 1024u) / (size_t)(max_ctas + 1) + 1;
+    return dyn_smem > floor_bytes ? dyn_smem : floor_bytes;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t sbo) {

@@ -180,3 +180,51 @@ def test_draw_reduction_matches_gen_range_outside_the_flagged_band():
         if not bad:
             assert v < ((1 << 64) - 16)                                     # accepted by Range::new(0, p - 1)
             assert (v & P) + 2 * (v >> 61) == v % (P - 1)
+
+
+# ---- packed_tc.cu: the persistent CTAs' walk over (participant, pass) units ------------------------
+def walk_units(grid, participants, unit_begin, units_per_p):
+    """packed_share_tc_kernel's unit bookkeeping: CTA x starts at unit x and strides by the grid; a launch
+    covers passes unit_begin .. unit_begin + units_per_p - 1 of every participant (the host entry point's slices)."""
+    unit_end = unit_begin + units_per_p
+    units_total = units_per_p * participants
+    seen = []
+    for cta in range(min(grid, units_total)):
+        p, u = cta // units_per_p, unit_begin + cta % units_per_p
+        unit = cta
+        while unit < units_total:
+            seen.append((p, u))
+            pn, un = p, u + grid
+            while un >= unit_end:
+                un -= units_per_p
+                pn += 1
+            p, u = pn, un
+            unit += grid
+    return seen
+
+
+def test_packed_tc_unit_walk_covers_every_slice_exactly_once():
+    rng = random.Random(5)
+    for _ in range(300):
+        grid = rng.choice([1, 2, 3, 7, 148, 592])
+        participants = rng.randint(1, 9)
+        units_per_p = rng.randint(1, 40)
+        unit_begin = rng.choice([0, 1, 5, 813])
+        seen = walk_units(grid, participants, unit_begin, units_per_p)
+        want = [(p, u) for p in range(participants) for u in range(unit_begin, unit_begin + units_per_p)]
+        assert sorted(seen) == want
+
+
+def test_host_slices_tile_the_vector():
+    """share_generate_sliced (csrc/api.cu): 16 slices, each a multiple of the kernel's pass size, cover [0, B)."""
+    for dim in (524_288, 600_001, 10_000_000, 25_000_000, 3 * 512 * 8 * 5):
+        k, unit, slices = 3, 512, 16
+        B = (dim + k - 1) // k
+        per = ((B + slices - 1) // slices + unit - 1) // unit * unit
+        covered, b0 = 0, 0
+        while b0 < B:
+            nb = min(per, B - b0)
+            assert b0 % unit == 0
+            covered += nb
+            b0 += per
+        assert covered == B and (B + per - 1) // per <= slices
