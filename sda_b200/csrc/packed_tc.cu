@@ -45,8 +45,9 @@ using namespace tc;
 #endif
 
 #ifndef SDA_TC_ACC_BUFS
-#define SDA_TC_ACC_BUFS 1   // 2: two TMEM accumulators (measured: 16.94 ms against 16.90 ms with one -- the kernel is bound by
-#endif                      //    instruction issue, not by waiting for the MMA; profiles/r01_k2_variants.md)
+#define SDA_TC_ACC_BUFS 2   // TMEM accumulators: 2 = the tiles of a pass go through the tensor core and the barriers in pairs
+                            // (16.54 ms against 17.18 ms with 1 on the same box, profiles/r01_k2_variants.md)
+#endif
 #ifndef SDA_TC_MINBLOCKS
 #define SDA_TC_MINBLOCKS 1
 #endif
@@ -80,9 +81,9 @@ struct Shape {
     static constexpr uint32_t B_BYTES = NMMA / 8 * SBO_B;
     static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + B_BYTES;
     static constexpr int ACC_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : NMMA <= 128 ? 128 : 256;
-    // optionally two TMEM accumulators (when that still leaves four CTAs per SM their columns): tile q + 2 is
-    // multiplied while tile q + 1 is composed, so nobody waits for an MMA
-    static constexpr int ACC_BUFS = (SDA_TC_ACC_BUFS >= 2 && 2 * ACC_COLS <= 128 && G >= 2) ? 2 : 1;
+    // optionally two TMEM accumulators (when that still leaves four CTAs per SM their columns): the tiles of a pass
+    // are multiplied, waited for and drained two at a time, which halves the barrier traffic per tile
+    static constexpr int ACC_BUFS = (SDA_TC_ACC_BUFS >= 2 && 2 * ACC_COLS <= 128 && G % 2 == 0) ? 2 : 1;
     static constexpr int TMEM_COLS = ACC_BUFS * ACC_COLS;
     static constexpr uint32_t IDESC = idesc_u8(NMMA);
     static_assert(4 % DC == 0, "a keystream block covers whole rows");
@@ -122,12 +123,14 @@ __device__ __forceinline__ void chacha_block(const uint32_t (&k)[8], uint64_t bl
 
 // draw (hi word w0, lo word w1) -> v mod (p - 1) as (v & p) + 2 (v >> 61).  That is gen_range's answer
 // unless v mod 2^61 >= 2^61 - 32 (a rejected word or a wrap-around).  The necessary condition "bits 32..60
-// all ones" (2^-29 per draw) is accumulated arithmetically -- hi + 1 carries into bit 29 exactly then -- so
-// it costs half an ALU instruction per draw, and the caller settles the rare case exactly.
+// all ones" (2^-29 per draw) is accumulated as the running maximum of the masked high words (one three-input
+// VIMNMX per two draws), and the caller settles the rare case `suspect >= 2^29 - 1` exactly.
 __device__ __forceinline__ uint64_t reduce_draw(uint32_t w0, uint32_t w1, uint32_t &suspect) {
-    const uint32_t h = w0 >> 29, hi = w0 & LOW29;
-    suspect |= hi + 1u;
-    return pack(w1, hi) + (uint64_t)(2u * h);
+    uint32_t h;
+    asm("shr.u32 %0, %1, 29;" : "=r"(h) : "r"(w0));       // kept apart from the doubling: (h << 1) + w1 is one LEA with carry
+    const uint32_t hi = w0 & LOW29;
+    suspect = max(suspect, hi);
+    return pack(w1, hi) + (uint64_t)(h << 1);
 }
 
 // ---- any prime below 2^63 -----------------------------------------------------------------------------
@@ -141,7 +144,7 @@ struct GenericField {
 
 __device__ __forceinline__ uint64_t reduce_draw_generic(const DrawParams &dr, uint32_t w0, uint32_t w1, uint32_t &suspect) {
     const uint64_t v = pack(w1, w0);
-    if (v >= dr.zone) suspect |= 1u << 29;                  // rejected by gen_range: the stream shifts, host redoes the call
+    if (v >= dr.zone) suspect = 0xffffffffu;                // rejected by gen_range: the stream shifts, host redoes the call
     return reduce64_generic(dr.f, v);
 }
 
@@ -161,7 +164,8 @@ static __device__ __noinline__ uint64_t canon_negative_generic(const FieldParams
 
 // one thread: the NK MMAs of a 128-row tile, completion signalled on `full_bar`
 template <class S>
-__device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_base, uint32_t full_bar) {
+__device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_base, uint32_t full_bar,
+                                           bool commit = true) {
     const uint64_t dd = umma_desc(d_tile, S::SBO_D), ds = umma_desc(s_tile, S::SBO_S), db = umma_desc(b_base, S::SBO_B);
 #pragma unroll
     for (int kk = 0; kk < S::NKD; kk++)
@@ -169,7 +173,16 @@ __device__ __forceinline__ void issue_tile(uint32_t taddr, uint32_t d_tile, uint
 #pragma unroll
     for (int kk = 0; kk < S::NKS; kk++)
         umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
+    if (commit) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
+}
+
+// the tiles q .. q + ACC_BUFS - 1 of a pass into the ACC_BUFS accumulators, one completion on `full_bar`
+template <class S>
+__device__ __forceinline__ void issue_tiles(uint32_t taddr, uint32_t d_cur, uint32_t s_base, uint32_t b_base, uint32_t full_bar, int q) {
+#pragma unroll
+    for (int a = 0; a < S::ACC_BUFS; a++)
+        issue_tile<S>(taddr + a * S::ACC_COLS, d_cur + (q + a) * S::D_TILE, s_base + (q + a) * S::S_TILE, b_base, full_bar,
+                      a == S::ACC_BUFS - 1);
 }
 
 // the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to
@@ -202,7 +215,7 @@ __device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, 
             *reinterpret_cast<uint4 *>(sD + q * S::D_TILE + (row >> 3) * S::SBO_D + c * LBO + (row & 7) * 16) =
                 make_uint4(xal, xah, xbl, xbh);
         }
-        if (suspect & (1u << 29)) {
+        if (suspect >= LOW29) {
             bool bad = !M61;
 #pragma unroll
             for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;
@@ -215,23 +228,42 @@ __device__ __forceinline__ void stage_draws(const ChaChaKey *__restrict__ keys, 
 // vector is zero padded (batched.rs:38-43)
 template <class S, int K>
 __device__ __forceinline__ void load_secrets(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t p, size_t u,
-                                             int tid, int64_t (&s)[S::G][2 * S::SC]) {
+                                             int tid, uint4 (&s)[S::G][S::SC]) {
+    // a row's secrets as the 16-byte chunks they are staged as: (x, y) = the even secret of the chunk, (z, w) = the odd
     const int64_t *sec = secrets + p * ld;
     const size_t b0 = u * (size_t)(S::G * CTA);
     const size_t e_first = (b0 + tid) * K;
     if ((b0 + (size_t)S::G * CTA) * K <= dim) {                                       // whole pass inside the vector
-        const int64_t *src = sec + e_first;
+        const uint2 *src = reinterpret_cast<const uint2 *>(sec + e_first);
 #pragma unroll
         for (int q = 0; q < S::G; q++)
 #pragma unroll
-            for (int i = 0; i < 2 * S::SC; i++) s[q][i] = i < K ? __ldg(src + q * (CTA * K) + i) : 0;
+            for (int c = 0; c < S::SC; c++) {
+                const uint2 a = __ldg(src + q * (CTA * K) + 2 * c);
+                const uint2 b = 2 * c + 1 < K ? __ldg(src + q * (CTA * K) + 2 * c + 1) : make_uint2(0, 0);
+                s[q][c] = make_uint4(a.x, a.y, b.x, b.y);
+            }
     } else {
 #pragma unroll
         for (int q = 0; q < S::G; q++) {
             const size_t e0 = e_first + (size_t)q * (CTA * K);
 #pragma unroll
-            for (int i = 0; i < 2 * S::SC; i++) s[q][i] = (i < K && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+            for (int c = 0; c < S::SC; c++) {
+                uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
+                if (e0 + 2 * c < dim) a = __ldg(reinterpret_cast<const uint2 *>(sec + e0 + 2 * c));
+                if (2 * c + 1 < K && e0 + 2 * c + 1 < dim) b = __ldg(reinterpret_cast<const uint2 *>(sec + e0 + 2 * c + 1));
+                s[q][c] = make_uint4(a.x, a.y, b.x, b.y);
+            }
         }
+    }
+}
+
+// a negative secret (sign bit in its high word) -> its canonical residue
+template <bool M61>
+__device__ __forceinline__ void canon_pair(uint32_t &lo, uint32_t &hi, const FieldParams &f) {
+    if ((int32_t)hi < 0) {
+        const int64_t v = (int64_t)pack(lo, hi);
+        unpack(M61 ? canon_negative(v) : canon_negative_generic(f, v), lo, hi);
     }
 }
 
@@ -245,7 +277,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     uint8_t *sD = smem;                                    // 2 x (G tiles x 128 rows x draws)
     uint8_t *sS = smem + 2 * S::D_BYTES;                   // G tiles x 128 rows x secrets
     uint8_t *sB = sS + S::S_BYTES;                         // the constant operand
-    __shared__ __align__(8) uint64_t mbar[4];              // [a] full (MMA into accumulator a done), [2 + a] drained (read out)
+    __shared__ __align__(8) uint64_t mbar[2];              // [0] full (MMAs done), [1] drained (TMEM read out)
     __shared__ uint32_t tmem_base;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -257,11 +289,8 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-#pragma unroll
-        for (int a = 0; a < 2; a++) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[a])) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[2 + a])), "n"(CTA) : "memory");
-        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "n"(CTA) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < S::B_BYTES / 16; i += CTA) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
@@ -271,10 +300,10 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base;
     const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
-    const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[2]);   // + 8 a
+    const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[1]);
     const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
     const size_t row_bytes = B * sizeof(int64_t);           // distance between the share rows of a participant
-    uint32_t phase = 0, buf = 0;                             // bit a: parity of the next phase of full[a] / drained[a]
+    uint32_t parity = 0, buf = 0;
 
     // (participant, pass) of this CTA's current unit and of its next one
     // (32-bit division: a 64-bit one is a call, and a call anywhere in the kernel makes ptxas keep the global
@@ -283,7 +312,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     // walks a vector in slices so that its copies overlap the kernel; device callers pass the whole vector)
     const size_t unit_end = unit_begin + units_per_p;
     size_t p = blockIdx.x / (uint32_t)units_per_p, u = unit_begin + blockIdx.x % (uint32_t)units_per_p;
-    int64_t s[S::G][2 * S::SC];                              // secrets of the coming pass, prefetched
+    uint4 s[S::G][S::SC];                                    // secrets of the coming pass, prefetched
     if (blockIdx.x < units_total) {
         load_secrets<S, K>(secrets, ld, dim, p, u, tid, s);
         stage_draws<S, ROUNDS, M61>(keys, p, u, tid, sD, gf, flag);
@@ -298,20 +327,17 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
             for (int q = 0; q < S::G; q++) {
                 uint32_t sign = 0;
 #pragma unroll
-                for (int i = 0; i < K; i++) sign |= (uint32_t)((uint64_t)s[q][i] >> 32);
+                for (int c = 0; c < S::SC; c++) sign |= s[q][c].y | s[q][c].w;
                 if ((int32_t)sign < 0) {
 #pragma unroll
-                    for (int i = 0; i < K; i++)
-                        if (s[q][i] < 0) s[q][i] = (int64_t)(M61 ? canon_negative(s[q][i]) : canon_negative_generic(gf.f, s[q][i]));
+                    for (int c = 0; c < S::SC; c++) {
+                        canon_pair<M61>(s[q][c].x, s[q][c].y, gf.f);
+                        canon_pair<M61>(s[q][c].z, s[q][c].w, gf.f);
+                    }
                 }
 #pragma unroll
-                for (int c = 0; c < S::SC; c++) {
-                    uint32_t al, ah, bl, bh;
-                    unpack((uint64_t)s[q][2 * c], al, ah);
-                    unpack((uint64_t)s[q][2 * c + 1], bl, bh);
-                    *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) =
-                        make_uint4(al, ah, bl, bh);
-                }
+                for (int c = 0; c < S::SC; c++)
+                    *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) = s[q][c];
             }
         }
         // rows complete: the secrets just written and the draws written during the previous pass
@@ -320,11 +346,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_cur = d_base + buf * S::D_BYTES;
-        if (tid == 0) {
-#pragma unroll
-            for (int a = 0; a < S::ACC_BUFS; a++)
-                issue_tile<S>(taddr + a * S::ACC_COLS, d_cur + a * S::D_TILE, s_base + a * S::S_TILE, b_base, full_bar + 8 * a);
-        }
+        if (tid == 0) issue_tiles<S>(taddr, d_cur, s_base, b_base, full_bar, 0);
 
         // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
         size_t pn = p, un = u + gridDim.x;
@@ -338,51 +360,46 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         if (more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
 
-        // ---- per tile: D = A . B^T on the tensor core, then compose the shares ------------------
-        // `full[a]` completes when a tile's MMAs have written accumulator a; `drained[a]` when all 128 threads
-        // have read their lane out of it.  With two accumulators thread 0 launches tile q + 2 after its own
-        // compose of tile q (by then the others have drained it too, so it does not spin) and the MMAs run
-        // under the compose of tile q + 1; with one, tile q + 1 is launched as soon as tile q is drained.
+        // ---- per group of ACC_BUFS tiles: D = A . B^T on the tensor core, then compose the shares -----------
+        // `full` completes when the group's MMAs have written TMEM; `drained` when all 128 threads have read
+        // their lanes out of it, so thread 0 can launch the next group's MMAs under everyone's (and its own)
+        // compose arithmetic of the group's last tile instead of after a CTA-wide barrier.
         // this thread's column of the share rows: batch b_first + q * CTA of tile q, live while it is below B
         const size_t b_first = b_base_batch + tid;
         char *ob = reinterpret_cast<char *>(out + p * (size_t)N * B + b_first);
         const size_t rows_left = b_first < B ? B - b_first : 0;
         const uint32_t live_rows = rows_left < (size_t)(S::G * CTA) ? (uint32_t)rows_left : (uint32_t)(S::G * CTA);
 #pragma unroll 1
-        for (int q = 0; q < S::G; q++) {
-            const uint32_t a = S::ACC_BUFS == 2 ? (uint32_t)(q & 1) : 0u;
-            const uint32_t par = (phase >> a) & 1u;
-            phase ^= 1u << a;
-            mbar_wait(full_bar + 8 * a, par);
+        for (int q = 0; q < S::G; q += S::ACC_BUFS) {
+            mbar_wait(full_bar, parity);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            uint32_t d[N][8];
 #pragma unroll
-            for (int j = 0; j < N; j++) tmem_ld8(my_taddr + a * S::ACC_COLS + 8 * j, d[j]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar + 8 * a) : "memory");
+            for (int a = 0; a < S::ACC_BUFS; a++) {
+                uint32_t d[N][8];
+                tmem_ld_shares<N>(my_taddr + a * S::ACC_COLS, d);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (a == S::ACC_BUFS - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
 #if SDA_TC_PREFETCH == 1
-            // next pass's secrets: issued under the last tile's compose arithmetic, consumed after it
-            if (q == S::G - 1 && more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
+                    // next pass's secrets: issued under the last tile's compose arithmetic, consumed after it
+                    if (q + S::ACC_BUFS >= S::G && more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
-            if (S::ACC_BUFS == 1 && tid == 0 && q + 1 < S::G) {
-                mbar_wait(drained_bar, par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_tile<S>(taddr, d_cur + (q + 1) * S::D_TILE, s_base + (q + 1) * S::S_TILE, b_base, full_bar);
-            }
-            const bool live = (uint32_t)(q * CTA) < live_rows;
+                    if (tid == 0 && q + S::ACC_BUFS < S::G) {
+                        mbar_wait(drained_bar, parity);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        issue_tiles<S>(taddr, d_cur, s_base, b_base, full_bar, q + S::ACC_BUFS);
+                    }
+                }
+                const bool live = (uint32_t)((q + a) * CTA) < live_rows;
 #pragma unroll
-            for (int j = 0; j < N; j++) {
-                const uint64_t r = M61 ? compose(d[j], two16) : compose_generic(d[j], two16, gf.f);
-                if (live) *reinterpret_cast<int64_t *>(ob + (size_t)j * row_bytes) = (int64_t)r;
+                for (int j = 0; j < N; j++) {
+                    const uint64_t r = M61 ? compose(d[j], two16) : compose_generic(d[j], two16, gf.f);
+                    if (live) *reinterpret_cast<int64_t *>(ob + (size_t)j * row_bytes) = (int64_t)r;
+                }
+                ob += CTA * sizeof(int64_t);
             }
-            ob += CTA * sizeof(int64_t);
-            if (S::ACC_BUFS == 2 && tid == 0 && q + 2 < S::G) {
-                mbar_wait(drained_bar + 8 * a, par);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                issue_tile<S>(taddr + a * S::ACC_COLS, d_cur + (q + 2) * S::D_TILE, s_base + (q + 2) * S::S_TILE, b_base,
-                              full_bar + 8 * a);
-            }
+            parity ^= 1;
         }
         // every thread is past its TMEM loads of the last tile and every MMA of this pass has completed
         // (`full` was waited on), so the next pass may overwrite the secrets and reuse TMEM
@@ -460,7 +477,7 @@ __device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ 
             *reinterpret_cast<uint4 *>(sD + warp * S::D_TILE + (row >> 3) * S::SBO_D + c * LBO + (row & 7) * 16) =
                 make_uint4(xal, xah, xbl, xbh);
         }
-        if (suspect & (1u << 29)) {
+        if (suspect >= LOW29) {
             bool bad = false;
 #pragma unroll
             for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;

@@ -60,6 +60,34 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr));
+}
+// the first 8 n columns of this thread's lane (n shares x 8 limb sums) in as few loads as powers of two allow
+template <int N>
+__device__ __forceinline__ void tmem_ld_shares(uint32_t taddr, uint32_t (&d)[N][8]) {
+    uint32_t *v = &d[0][0];
+    int c = 0;
+#pragma unroll
+    for (; c + 32 <= 8 * N; c += 32) tmem_ld32(taddr + c, v + c);
+    if (8 * N - c >= 16) {
+        tmem_ld16(taddr + c, v + c);
+        c += 16;
+    }
+    if (8 * N - c >= 8) tmem_ld8(taddr + c, *reinterpret_cast<uint32_t (*)[8]>(v + c));
+}
 __device__ __forceinline__ uint64_t pack(uint32_t lo, uint32_t hi) {
     uint64_t d;
     asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
