@@ -486,15 +486,21 @@ __device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ 
     }
 }
 
-// the K secrets of batch b of participants p0 .. p0 + GP - 1 (zero beyond P and beyond the vector)
+// the K secrets of batch b of participants p0 .. p0 + GP - 1 (zero beyond P and beyond the vector), as the
+// 16-byte chunks they are staged as
 template <class F, int K>
 __device__ __forceinline__ void load_secrets_fused(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t P,
-                                                   size_t p0, size_t e0, int64_t (&s)[F::GP][2 * F::S::SC]) {
+                                                   size_t p0, size_t e0, uint4 (&s)[F::GP][F::S::SC]) {
 #pragma unroll
     for (int q = 0; q < F::GP; q++) {
         const int64_t *sec = secrets + (p0 + q) * ld;
 #pragma unroll
-        for (int i = 0; i < 2 * F::S::SC; i++) s[q][i] = (i < K && p0 + q < P && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+        for (int c = 0; c < F::S::SC; c++) {
+            uint2 a = make_uint2(0, 0), b = make_uint2(0, 0);
+            if (p0 + q < P && e0 + 2 * c < dim) a = __ldg(reinterpret_cast<const uint2 *>(sec + e0 + 2 * c));
+            if (2 * c + 1 < K && p0 + q < P && e0 + 2 * c + 1 < dim) b = __ldg(reinterpret_cast<const uint2 *>(sec + e0 + 2 * c + 1));
+            s[q][c] = make_uint4(a.x, a.y, b.x, b.y);
+        }
     }
 }
 
@@ -536,7 +542,7 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
     const size_t ranges = (B + CTA - 1) / CTA;
     const size_t groups = (P + F::GP - 1) / F::GP;
     // keystream and secrets of the first pass
-    int64_t s[F::GP][2 * S::SC];
+    uint4 s[F::GP][S::SC];
     if (blockIdx.x < ranges) {
         load_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, s);
         if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
@@ -560,17 +566,20 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
 #pragma unroll
             for (int q = 0; q < F::GP; q++) {
                 if (q < np) {
+                    uint32_t sign = 0;
 #pragma unroll
-                    for (int i = 0; i < K; i++)
-                        if (s[q][i] < 0) s[q][i] = (int64_t)canon_negative(s[q][i]);
+                    for (int c = 0; c < S::SC; c++) sign |= s[q][c].y | s[q][c].w;
+                    if ((int32_t)sign < 0) {
+                        const FieldParams unused{};
 #pragma unroll
-                    for (int c = 0; c < S::SC; c++) {
-                        uint32_t al, ah, bl, bh;
-                        unpack((uint64_t)s[q][2 * c], al, ah);
-                        unpack((uint64_t)s[q][2 * c + 1], bl, bh);
-                        *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) =
-                            make_uint4(al, ah, bl, bh);
+                        for (int c = 0; c < S::SC; c++) {
+                            canon_pair<true>(s[q][c].x, s[q][c].y, unused);
+                            canon_pair<true>(s[q][c].z, s[q][c].w, unused);
+                        }
                     }
+#pragma unroll
+                    for (int c = 0; c < S::SC; c++)
+                        *reinterpret_cast<uint4 *>(sS + q * S::S_TILE + (tid >> 3) * S::SBO_S + c * LBO + (tid & 7) * 16) = s[q][c];
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
