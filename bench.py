@@ -218,9 +218,12 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line.  NCCL printf()s its "NCCL version ..." banner to fd 1 (this image sets
+    # NCCL_DEBUG=VERSION; NCCL_DEBUG_FILE does not move it), so fd 1 is pointed at stderr for the duration of the
+    # run and the JSON line goes to a private duplicate of the original stdout.
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
@@ -449,7 +452,8 @@ def run_ours(args):
                 "participants_per_step": Te, "api": "sda_share_generate per participant + sda_share_combine_rows per clerk (pinned host buffers)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    json_out.write(json.dumps(line) + "\n")
+    json_out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
