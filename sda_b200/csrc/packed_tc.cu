@@ -48,6 +48,9 @@ using namespace tc;
 #define SDA_TC_ACC_BUFS 2   // TMEM accumulators: 2 = the tiles of a pass go through the tensor core and the barriers in pairs
                             // (16.54 ms against 17.18 ms with 1 on the same box, profiles/r01_k2_variants.md)
 #endif
+#ifndef SDA_TC_BULK_IN
+#define SDA_TC_BULK_IN 1    // secrets of a pass arrive in shared memory by one bulk copy (TMA unit) instead of 12 loads per thread
+#endif
 #ifndef SDA_TC_MINBLOCKS
 #define SDA_TC_MINBLOCKS 1
 #endif
@@ -79,7 +82,9 @@ struct Shape {
     static constexpr int NMMA = (8 * N + 15) / 16 * 16;
     static constexpr uint32_t SBO_B = 2 * NK * 128;
     static constexpr uint32_t B_BYTES = NMMA / 8 * SBO_B;
-    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + B_BYTES;
+    // the raw secrets of one pass, [G x 128 batches][K] i64 exactly as they lie in the participant's vector
+    static constexpr uint32_t IN_BYTES = SDA_TC_BULK_IN ? G * 128 * K * 8 : 0;
+    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + B_BYTES + IN_BYTES;
     static constexpr int ACC_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : NMMA <= 128 ? 128 : 256;
     // optionally two TMEM accumulators (when that still leaves four CTAs per SM their columns): the tiles of a pass
     // are multiplied, waited for and drained two at a time, which halves the barrier traffic per tile
@@ -88,6 +93,7 @@ struct Shape {
     static constexpr uint32_t IDESC = idesc_u8(NMMA);
     static_assert(4 % DC == 0, "a keystream block covers whole rows");
     static_assert(D_BYTES % 128 == 0 && S_BYTES % 128 == 0, "operand buffers stay 128-byte aligned");
+    static_assert(B_BYTES % 16 == 0 && IN_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes to 16-byte aligned addresses");
 };
 
 #define SDA_QR(a, b, c, d)                                      \
@@ -258,6 +264,33 @@ __device__ __forceinline__ void load_secrets(const int64_t *__restrict__ secrets
     }
 }
 
+// The same rows into the pass's shared-memory staging buffer, by the threads themselves: the path of a pass that
+// is not wholly inside the vector (zero padding, batched.rs:38-43) or whose source is not 16-byte aligned.  Every
+// thread writes, and later reads, only its own K words per tile.
+template <class S, int K>
+__device__ __forceinline__ void fill_secrets(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t p, size_t u,
+                                             int tid, int64_t *sIn) {
+    const int64_t *sec = secrets + p * ld;
+    const size_t e_first = (u * (size_t)(S::G * CTA) + tid) * K;
+#pragma unroll
+    for (int q = 0; q < S::G; q++) {
+        const size_t e0 = e_first + (size_t)q * (CTA * K);
+#pragma unroll
+        for (int i = 0; i < K; i++) sIn[(q * CTA + tid) * K + i] = e0 + i < dim ? __ldg(sec + e0 + i) : 0;
+    }
+}
+
+// One thread: the whole pass -- G x 128 batches x K secrets, contiguous in the participant's vector -- into the
+// staging buffer with one bulk copy; completion (by byte count) on `bar`.
+template <class S, int K>
+__device__ __forceinline__ void bulk_load_secrets(const int64_t *__restrict__ secrets, size_t ld, size_t p, size_t u,
+                                                  uint32_t sin_addr, uint32_t bar) {
+    const int64_t *src = secrets + p * ld + u * (size_t)(S::G * CTA) * K;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(S::IN_BYTES) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(sin_addr), "l"(src), "r"(S::IN_BYTES), "r"(bar) : "memory");
+}
+
 // a negative secret (sign bit in its high word) -> its canonical residue
 template <bool M61>
 __device__ __forceinline__ void canon_pair(uint32_t &lo, uint32_t &hi, const FieldParams &f) {
@@ -271,13 +304,15 @@ template <int K, int T, int N, int ROUNDS, bool M61>
 __global__ void __launch_bounds__(CTA, SDA_TC_MINBLOCKS)
 packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t unit_begin, size_t units_per_p,
                        size_t units_total, const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
-                       int64_t *__restrict__ out, uint32_t two16, const __grid_constant__ GenericField gf, unsigned *flag) {
+                       int64_t *__restrict__ out, uint32_t two16, const __grid_constant__ GenericField gf, unsigned *flag,
+                       int bulk_ok) {
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (G tiles x 128 rows x draws)
     uint8_t *sS = smem + 2 * S::D_BYTES;                   // G tiles x 128 rows x secrets
     uint8_t *sB = sS + S::S_BYTES;                         // the constant operand
-    __shared__ __align__(8) uint64_t mbar[2];              // [0] full (MMAs done), [1] drained (TMEM read out)
+    int64_t *sIn = reinterpret_cast<int64_t *>(sB + S::B_BYTES);   // the coming pass's raw secrets (SDA_TC_BULK_IN)
+    __shared__ __align__(8) uint64_t mbar[3];              // [0] full (MMAs done), [1] drained (TMEM read out), [2] secrets landed
     __shared__ uint32_t tmem_base;
 
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -291,6 +326,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "n"(CTA) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[2])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < S::B_BYTES / 16; i += CTA) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
@@ -302,8 +338,11 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
     const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[1]);
     const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
+    const uint32_t landed_bar = smem_u32(&mbar[2]), sin_addr = smem_u32(sIn);
     const size_t row_bytes = B * sizeof(int64_t);           // distance between the share rows of a participant
-    uint32_t parity = 0, buf = 0;
+    uint32_t parity = 0, buf = 0, landed_parity = 0;
+    // a pass that lies wholly inside its vector arrives by bulk copy when the source is 16-byte aligned (bulk_ok)
+    auto by_bulk = [&](size_t uu) { return bulk_ok != 0 && (uu + 1) * (size_t)(S::G * CTA) * K <= dim; };
 
     // (participant, pass) of this CTA's current unit and of its next one
     // (32-bit division: a 64-bit one is a call, and a call anywhere in the kernel makes ptxas keep the global
@@ -312,17 +351,46 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
     // walks a vector in slices so that its copies overlap the kernel; device callers pass the whole vector)
     const size_t unit_end = unit_begin + units_per_p;
     size_t p = blockIdx.x / (uint32_t)units_per_p, u = unit_begin + blockIdx.x % (uint32_t)units_per_p;
+#if SDA_TC_BULK_IN
+    if (blockIdx.x < units_total) {
+        if (by_bulk(u)) {
+            if (tid == 0) bulk_load_secrets<S, K>(secrets, ld, p, u, sin_addr, landed_bar);
+        } else {
+            fill_secrets<S, K>(secrets, ld, dim, p, u, tid, sIn);
+        }
+        stage_draws<S, ROUNDS, M61>(keys, p, u, tid, sD, gf, flag);
+    }
+#else
     uint4 s[S::G][S::SC];                                    // secrets of the coming pass, prefetched
     if (blockIdx.x < units_total) {
         load_secrets<S, K>(secrets, ld, dim, p, u, tid, s);
         stage_draws<S, ROUNDS, M61>(keys, p, u, tid, sD, gf, flag);
     }
+#endif
 
     for (size_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
         const size_t b_base_batch = u * (size_t)(S::G * CTA);
         // ---- secrets of row `tid` of every tile (loaded during the previous pass): their little-endian
         //      bytes are the limbs ----------------------------------------------------------------------
         {
+#if SDA_TC_BULK_IN
+            // the pass's raw secrets are in shared memory (bulk copy issued a pass ago, or this thread's own stores)
+            if (by_bulk(u)) {
+                mbar_wait(landed_bar, landed_parity);
+                landed_parity ^= 1;
+            }
+            uint4 s[S::G][S::SC];
+#pragma unroll
+            for (int q = 0; q < S::G; q++) {
+                const int64_t *row = sIn + (q * CTA + tid) * K;
+#pragma unroll
+                for (int c = 0; c < S::SC; c++) {
+                    const uint2 a = *reinterpret_cast<const uint2 *>(row + 2 * c);
+                    const uint2 b = 2 * c + 1 < K ? *reinterpret_cast<const uint2 *>(row + 2 * c + 1) : make_uint2(0, 0);
+                    s[q][c] = make_uint4(a.x, a.y, b.x, b.y);
+                }
+            }
+#endif
 #pragma unroll
             for (int q = 0; q < S::G; q++) {
                 uint32_t sign = 0;
@@ -346,17 +414,25 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_cur = d_base + buf * S::D_BYTES;
-        if (tid == 0) issue_tiles<S>(taddr, d_cur, s_base, b_base, full_bar, 0);
-
-        // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
-        size_t pn = p, un = u + gridDim.x;
+        size_t pn = p, un = u + gridDim.x;                   // this CTA's next unit
         while (un >= unit_end) {
             un -= units_per_p;
             pn++;
         }
         const bool more = unit + gridDim.x < units_total;
+        if (tid == 0) {
+            issue_tiles<S>(taddr, d_cur, s_base, b_base, full_bar, 0);
+#if SDA_TC_BULK_IN
+            // everyone is past the barrier, i.e. has read this pass's raw secrets: the next pass's may land
+            if (more && by_bulk(un)) bulk_load_secrets<S, K>(secrets, ld, pn, un, sin_addr, landed_bar);
+#endif
+        }
+
+        // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
         if (more) stage_draws<S, ROUNDS, M61>(keys, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, gf, flag);
-#if SDA_TC_PREFETCH == 2
+#if SDA_TC_BULK_IN
+        if (more && !by_bulk(un)) fill_secrets<S, K>(secrets, ld, dim, pn, un, tid, sIn);
+#elif SDA_TC_PREFETCH == 2
         if (more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
 
@@ -381,7 +457,7 @@ packed_share_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t di
                 if (a == S::ACC_BUFS - 1) {
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
-#if SDA_TC_PREFETCH == 1
+#if !SDA_TC_BULK_IN && SDA_TC_PREFETCH == 1
                     // next pass's secrets: issued under the last tile's compose arithmetic, consumed after it
                     if (q + S::ACC_BUFS >= S::G && more) load_secrets<S, K>(secrets, ld, dim, pn, un, tid, s);
 #endif
@@ -696,8 +772,10 @@ cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *s
     }
     size_t grid = (size_t)lc.sm_count * per_sm;
     if (grid > units_total) grid = units_total;
+    // bulk copies need 16-byte aligned sources: every pass of every participant starts at an even element
+    const int bulk_ok = SDA_TC_BULK_IN && reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, unit_begin, units_per_p, units_total, keys,
-                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, gf, flag);
+                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, gf, flag, bulk_ok);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
