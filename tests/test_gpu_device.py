@@ -68,6 +68,37 @@ def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
         ctx.set_packed_path(0)
 
 
+@pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
+@pytest.mark.parametrize("offset,ld_pad", [(0, 0), (1, 0), (0, 1), (1, 1), (2, 2)])
+def test_packed_tc_secret_sources_of_every_alignment(ctx, oracle, torch_cuda, mk, offset, ld_pad):
+    """the tensor-core kernel takes a pass's secrets by bulk copy when the source is 16-byte aligned and every
+    participant starts at an even element, and by per-thread loads otherwise: same shares either way"""
+    t = torch_cuda
+    s = mk()
+    k = s.input_size()
+    P, dim = 3, 5 * 512 * k + 2 * k + 1          # interior passes and a ragged last one
+    ld = dim + (dim & 1) + ld_pad                # even (+ pad): odd strides break the alignment of participants 1, 2
+    rng = np.random.default_rng(offset * 10 + ld_pad)
+    secrets = rng.integers(0, s.modulus, size=(P, dim), dtype=np.int64)
+    secrets[1, ::11] = rng.integers(-(1 << 63), 1 << 63, size=secrets[1, ::11].shape, dtype=np.int64)
+    flat = np.zeros(offset + P * ld, dtype=np.int64)
+    for pi in range(P):
+        flat[offset + pi * ld: offset + pi * ld + dim] = secrets[pi]
+    d_flat = dev(t, flat)
+    d_in = d_flat[offset:]                       # data pointer 8 * offset bytes past a 256-byte aligned allocation
+    assert (d_in.data_ptr() % 16 == 0) == (offset % 2 == 0)
+    n, B = s.output_size(), s.batches(dim)
+    seeds = b"".join(util.seed_bytes(f"align/{offset}/{ld_pad}/{pi}") for pi in range(P))
+    d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+    ctx.share_generate_dev(s, d_in, ld, P, dim, seeds, d_out)
+    ctx.synchronize()
+    assert "tcgen05" in ctx.last_kernel()
+    got = host(d_out)
+    for pi in range(P):
+        exp = util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)
+        assert np.array_equal(got[pi], util.canon(oracle, s.modulus, exp)), (offset, ld_pad, pi)
+
+
 @pytest.mark.parametrize("mk", [params.config2, params.config3, params.config4, params.config5,
                                 lambda: LSS.Additive(3, 433), params.reference_test])
 def test_share_generate_dev_multi_participant(ctx, oracle, torch_cuda, mk):
