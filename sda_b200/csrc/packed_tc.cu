@@ -507,7 +507,10 @@ struct FusedShape : Shape<K, T, N> {
     static constexpr int GP = 4;                               // participants per pass (one per warp)
     static constexpr int NBW = T / 2;                          // keystream blocks per lane per pass
     static constexpr uint32_t D_BYTES = GP * S::D_TILE + 128, S_BYTES = GP * S::S_TILE + 128;
-    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + S::B_BYTES;
+    // the raw secrets of one pass: GP participants x [128 batches][K] i64, each block contiguous in its vector
+    static constexpr uint32_t IN_ROW_BYTES = 128 * K * 8;
+    static constexpr uint32_t IN_BYTES = SDA_TC_BULK_IN ? GP * IN_ROW_BYTES : 0;
+    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + S::B_BYTES + IN_BYTES;
     static constexpr int TMEM_COLS = S::NMMA <= 32 ? 32 : S::NMMA <= 64 ? 64 : 128;
     static constexpr int MAX_ACCUM = 256;                      // participants per TMEM accumulation: 256 * 96 * 255^2 < 2^31
 };
@@ -580,18 +583,44 @@ __device__ __forceinline__ void load_secrets_fused(const int64_t *__restrict__ s
     }
 }
 
+// the same rows into the pass's staging buffer by the threads themselves (ragged last range, unaligned sources)
+template <class F, int K>
+__device__ __forceinline__ void fill_secrets_fused(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t P,
+                                                   size_t p0, size_t e0, int tid, int64_t *sIn) {
+#pragma unroll
+    for (int q = 0; q < F::GP; q++) {
+        const int64_t *sec = secrets + (p0 + q) * ld;
+#pragma unroll
+        for (int i = 0; i < K; i++)
+            sIn[q * (CTA * K) + tid * K + i] = (p0 + q < P && e0 + i < dim) ? __ldg(sec + e0 + i) : 0;
+    }
+}
+
+// one thread: batch range r of participants p0 .. p0 + np - 1, one bulk copy each, completion by byte count on `bar`
+template <class F, int K>
+__device__ __forceinline__ void bulk_load_secrets_fused(const int64_t *__restrict__ secrets, size_t ld, size_t p0, int np,
+                                                        size_t r, uint32_t sin_addr, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(np * F::IN_ROW_BYTES) : "memory");
+    for (int q = 0; q < np; q++) {
+        const int64_t *src = secrets + (p0 + q) * ld + r * (size_t)(CTA * K);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(sin_addr + q * F::IN_ROW_BYTES), "l"(src), "r"(F::IN_ROW_BYTES), "r"(bar) : "memory");
+    }
+}
+
 template <int K, int T, int N, int ROUNDS>
 __global__ void __launch_bounds__(CTA)
 packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t P,
                                const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
-                               const int64_t *__restrict__ acc_in, int64_t *__restrict__ out, unsigned *flag) {
+                               const int64_t *__restrict__ acc_in, int64_t *__restrict__ out, unsigned *flag, int bulk_ok) {
     typedef FusedShape<K, T, N> F;
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (4 participants x 128 rows x draws)
     uint8_t *sS = smem + 2 * F::D_BYTES;                   // 4 participants x 128 rows x secrets
     uint8_t *sB = sS + F::S_BYTES;
-    __shared__ __align__(8) uint64_t mbar;
+    int64_t *sIn = reinterpret_cast<int64_t *>(sB + S::B_BYTES);   // the coming pass's raw secrets (SDA_TC_BULK_IN)
+    __shared__ __align__(8) uint64_t mbar, landed;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -602,6 +631,7 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
     }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&landed)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (uint32_t i = tid; i < S::B_BYTES / 16; i += CTA) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
@@ -611,18 +641,32 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = tmem_base;
     const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
-    const uint32_t full_bar = smem_u32(&mbar);
+    const uint32_t full_bar = smem_u32(&mbar), landed_bar = smem_u32(&landed), sin_addr = smem_u32(sIn);
     const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB);
-    uint32_t parity = 0, buf = 0;
+    uint32_t parity = 0, buf = 0, landed_parity = 0;
 
     const size_t ranges = (B + CTA - 1) / CTA;
     const size_t groups = (P + F::GP - 1) / F::GP;
+    // a batch range that lies wholly inside the vectors arrives by bulk copy when the sources are 16-byte aligned
+    auto by_bulk = [&](size_t rr) { return bulk_ok != 0 && (rr + 1) * (size_t)(CTA * K) <= dim; };
+    auto participants_of = [&](size_t pg) { return (int)(P - pg < (size_t)F::GP ? P - pg : F::GP); };
     // keystream and secrets of the first pass
+#if SDA_TC_BULK_IN
+    if (blockIdx.x < ranges) {
+        if (by_bulk(blockIdx.x)) {
+            if (tid == 0) bulk_load_secrets_fused<F, K>(secrets, ld, 0, participants_of(0), blockIdx.x, sin_addr, landed_bar);
+        } else {
+            fill_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, tid, sIn);
+        }
+        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+    }
+#else
     uint4 s[F::GP][S::SC];
     if (blockIdx.x < ranges) {
         load_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, s);
         if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
     }
+#endif
 
     for (size_t r = blockIdx.x; r < ranges; r += gridDim.x) {
         const size_t b = r * CTA + tid;                    // this thread's batch
@@ -639,6 +683,26 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
             const size_t p0 = g * F::GP;
             const int np = (int)(P - p0 < (size_t)F::GP ? P - p0 : F::GP);
             // ---- secrets of batch b of the np participants: their bytes are the limbs -----------
+#if SDA_TC_BULK_IN
+            if (by_bulk(r)) {
+                mbar_wait(landed_bar, landed_parity);
+                landed_parity ^= 1;
+            }
+            uint4 s[F::GP][S::SC];
+#pragma unroll
+            for (int q = 0; q < F::GP; q++) {
+                const int64_t *row = sIn + q * (CTA * K) + tid * K;
+#pragma unroll
+                for (int c = 0; c < S::SC; c++) {
+                    uint2 a = make_uint2(0, 0), b2 = make_uint2(0, 0);
+                    if (q < np) {
+                        a = *reinterpret_cast<const uint2 *>(row + 2 * c);
+                        if (2 * c + 1 < K) b2 = *reinterpret_cast<const uint2 *>(row + 2 * c + 1);
+                    }
+                    s[q][c] = make_uint4(a.x, a.y, b2.x, b2.y);
+                }
+            }
+#endif
 #pragma unroll
             for (int q = 0; q < F::GP; q++) {
                 if (q < np) {
@@ -677,7 +741,7 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
             }
             in_tmem += np;
-            // ---- the next pass's keystream (next participants of this range, or the next range) under the MMAs
+            // ---- the next pass's secrets and keystream (next participants of this range, or the next range) under the MMAs
             {
                 size_t rn = r, pg = p0 + F::GP;
                 if (g + 1 == groups) {
@@ -685,7 +749,16 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
                     pg = 0;
                 }
                 if (rn < ranges) {
+#if SDA_TC_BULK_IN
+                    // everyone is past the barrier, i.e. has read this pass's raw secrets: the next pass's may land
+                    if (by_bulk(rn)) {
+                        if (tid == 0) bulk_load_secrets_fused<F, K>(secrets, ld, pg, participants_of(pg), rn, sin_addr, landed_bar);
+                    } else {
+                        fill_secrets_fused<F, K>(secrets, ld, dim, P, pg, (rn * CTA + tid) * K, tid, sIn);
+                    }
+#else
                     load_secrets_fused<F, K>(secrets, ld, dim, P, pg, (rn * CTA + tid) * K, s);     // consumed after the keystream
+#endif
                     if (pg + warp < P) stage_draws_fused<F, ROUNDS>(keys, pg + warp, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
                 }
             }
@@ -818,8 +891,9 @@ cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld,
         per_sm = std::max(1, std::min(by_regs, std::min(by_smem, 512 / F::TMEM_COLS)));
     }
     const size_t grid = std::min<size_t>(ranges, (size_t)lc.sm_count * per_sm);
+    const int bulk_ok = SDA_TC_BULK_IN && reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, P, keys, reinterpret_cast<const uint4 *>(d_b_image),
-                                                   acc_in, out, flag);
+                                                   acc_in, out, flag, bulk_ok);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
