@@ -831,18 +831,12 @@ cudaError_t launch(const LaunchCtx &lc, const GenericField &gf, const int64_t *s
     auto kern = packed_share_tc_kernel<K, T, N, ROUNDS, M61>;
     // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh)
     const size_t smem = smem_capping_residency(S::SMEM, 512 / S::TMEM_COLS);
-    static int per_sm = 0;      // resident CTAs per SM
-    if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncAttributes fa;
-        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
-        if (e != cudaSuccess) return e;
-        const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * CTA);
-        const int by_smem = (int)((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
-        const int by_tmem = 512 / S::TMEM_COLS;
-        per_sm = std::max(1, std::min(by_regs, std::min(by_smem, by_tmem)));
-    }
+    static KernelSetup setup;
+    int regs = 0;
+    size_t static_smem = 0;
+    const cudaError_t se = setup_kernel(setup, kern, smem, &regs, &static_smem);
+    if (se != cudaSuccess) return se;
+    const int per_sm = resident_ctas(regs, CTA, smem, static_smem, S::TMEM_COLS);
     size_t grid = (size_t)lc.sm_count * per_sm;
     if (grid > units_total) grid = units_total;
     // bulk copies need 16-byte aligned sources: every pass of every participant starts at an even element
@@ -879,17 +873,12 @@ cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld,
     const size_t ranges = (B + CTA - 1) / CTA;
     const size_t smem = smem_capping_residency(F::SMEM, 512 / F::TMEM_COLS);
     auto kern = packed_share_combine_tc_kernel<K, T, N, ROUNDS>;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncAttributes fa;
-        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
-        if (e != cudaSuccess) return e;
-        const int by_regs = 65536 / (((fa.numRegs + 7) & ~7) * CTA);
-        const int by_smem = (int)((227u * 1024u) / (smem + fa.sharedSizeBytes + 1024));
-        per_sm = std::max(1, std::min(by_regs, std::min(by_smem, 512 / F::TMEM_COLS)));
-    }
+    static KernelSetup setup;
+    int regs = 0;
+    size_t static_smem = 0;
+    const cudaError_t se = setup_kernel(setup, kern, smem, &regs, &static_smem);
+    if (se != cudaSuccess) return se;
+    const int per_sm = resident_ctas(regs, CTA, smem, static_smem, F::TMEM_COLS);
     const size_t grid = std::min<size_t>(ranges, (size_t)lc.sm_count * per_sm);
     const int bulk_ok = SDA_TC_BULK_IN && reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, P, keys, reinterpret_cast<const uint4 *>(d_b_image),

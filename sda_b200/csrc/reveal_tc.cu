@@ -163,20 +163,12 @@ cudaError_t launch(const LaunchCtx &lc, const RevealShape &s, const int64_t *sha
     // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh): this kernel needs few registers
     // and little shared memory, so without the floor 12 CTAs land on an SM that has columns for 512 / TMEM_COLS
     const size_t smem = smem_capping_residency(((s.a_bytes + 127) & ~127u) + s.b_bytes, 512 / TMEM_COLS);
-    static size_t smem_set = 0;
-    static int regs = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64 * 1024));
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncAttributes fa;
-        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
-        if (e != cudaSuccess) return e;
-        regs = fa.numRegs;
-        smem_set = std::max<size_t>(smem, 64 * 1024);
-    }
-    const int by_regs = 65536 / (((regs + 7) & ~7) * CTA);
-    const int by_smem = (int)((227u * 1024u) / (smem + 1024 + 128));
-    const int per_sm = std::max(1, std::min(by_regs, std::min(by_smem, 512 / TMEM_COLS)));
+    static KernelSetup setup;                              // one per TMEM size (this function is a template)
+    int regs = 0;
+    size_t static_smem = 0;
+    const cudaError_t se = setup_kernel(setup, kern, 100 * 1024, &regs, &static_smem);    // any shape's request fits
+    if (se != cudaSuccess) return se;
+    const int per_sm = resident_ctas(regs, CTA, smem, static_smem, TMEM_COLS);
     const size_t tiles = (nbatches + CTA - 1) / CTA;
     const size_t grid = std::min<size_t>(tiles, (size_t)lc.sm_count * per_sm);
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(shares, ld, nbatches, dimension, s.k, s.m, s.chunks, s.nk, s.sbo_a,

@@ -8,6 +8,7 @@
 // One MMA consumes 32 bytes of K = two chunks.  tools/tc_probe.cu checks this encoding against a host GEMM.
 #pragma once
 #include <cstdint>
+#include <mutex>
 
 #include "field.cuh"
 
@@ -30,6 +31,45 @@ __host__ __device__ constexpr uint32_t idesc_u8(int n_mma) {
 inline size_t smem_capping_residency(size_t dyn_smem, int max_ctas) {
     const size_t floor_bytes = (228u * 1024u) / (size_t)(max_ctas + 1) + 1;
     return dyn_smem > floor_bytes ? dyn_smem : floor_bytes;
+}
+
+// Function attributes are per device and the host entry points may be called from several threads (one context
+// each): raise a kernel's dynamic shared-memory limit once per device, under a lock, and remember what the
+// occupancy arithmetic needs.
+struct KernelSetup {
+    std::mutex mu;
+    bool done[64] = {};
+    int regs[64] = {};
+    size_t static_smem[64] = {};
+};
+template <class Kern>
+inline cudaError_t setup_kernel(KernelSetup &ks, Kern kern, size_t max_dyn_smem, int *regs, size_t *static_smem) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(ks.mu);
+    if (!ks.done[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncAttributes fa;
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        ks.regs[dev] = fa.numRegs;
+        ks.static_smem[dev] = fa.sharedSizeBytes;
+        ks.done[dev] = true;
+    }
+    *regs = ks.regs[dev];
+    *static_smem = ks.static_smem[dev];
+    return cudaSuccess;
+}
+// CTAs of `threads` threads an SM can hold, given registers, shared memory and TMEM columns per CTA
+inline int resident_ctas(int regs, int threads, size_t dyn_smem, size_t static_smem, int tmem_cols) {
+    const int by_regs = 65536 / (((regs + 7) & ~7) * threads);
+    const int by_smem = (int)((227u * 1024u) / (dyn_smem + static_smem + 1024));
+    const int by_tmem = 512 / tmem_cols;
+    const int n = by_regs < by_smem ? by_regs : by_smem;
+    return n < by_tmem ? (n > 1 ? n : 1) : by_tmem;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
