@@ -131,27 +131,75 @@ def run_reference(args):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi polled every 25 ms from before the warm-up; stop(t0, t1) keeps the samples whose timestamps
-    fall inside the timed region [t0, t1] (wall clock), falling back to every sample taken under load
-    (warm-up + timed steps run the same kernels back to back) when the region is too short to hold two."""
+    """SM clock, power and clock-event reasons of one GPU, polled every 5 ms from a thread of this process through
+    NVML (pynvml) from before the warm-up; stop(t0, t1) keeps the samples whose timestamps fall inside the timed
+    region [t0, t1] (wall clock).  If NVML cannot be loaded the same query runs as an `nvidia-smi -lms 25` child.
+    A region too short to hold two samples falls back to every sample taken under load (warm-up + timed steps run
+    the same kernels back to back) and says so in `window`."""
     QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
+        self.rows = []                 # (wall time, sm MHz, max sm MHz, power W, [reasons])
+        self.p = self.f = self.thread = None
+        self.source = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if pci_bus_id:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id)
+                except Exception:
+                    h = None
+            if h is None:
+                h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            names = (("hw_slowdown", pynvml.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", pynvml.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", pynvml.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", pynvml.nvmlClocksEventReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", pynvml.nvmlClocksEventReasonHwPowerBrakeSlowdown))
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.rows.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), sm_max,
+                                          pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0, [n for n, bit in names if mask & bit]))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.005)
+
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            self.source = "NVML, 5 ms polling"
+            return
+        except Exception:
+            self.thread = None
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
                                        "-lms", "25", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi -lms 25"
         except OSError:
             self.p = None
 
-    def stop(self, t0, t1):
+    def ready(self, timeout=3.0):
+        """block until the first sample exists (nvidia-smi needs a moment to start; NVML is immediate)"""
+        t_end = time.time() + timeout
+        while time.time() < t_end:
+            if self.rows or (self.f is not None and os.path.getsize(self.f.name) > 0):
+                return True
+            time.sleep(0.01)
+        return False
+
+    def _collect_smi(self):
         import datetime
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
-            return out
+            return
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -159,16 +207,15 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        rows = []
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
             if len(parts) < 10:
                 continue
             try:
                 ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]),
-                             [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                                parts[6:10]) if v.lower().startswith("active")]))
+                self.rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]),
+                                  [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                                     parts[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
         self.f.close()
@@ -176,9 +223,18 @@ class ClockSampler:
             os.unlink(self.f.name)
         except OSError:
             pass
+
+    def stop(self, t0, t1):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": self.source}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        else:
+            self._collect_smi()
+        rows = list(self.rows)
         inside = [r for r in rows if t0 <= r[0] <= t1]
         window = "timed region"
-        if len(inside) < 2:          # a ~100 ms region holds few 25 ms samples: use everything under load since warm-up
+        if len(inside) < 2:          # use everything under load since the warm-up
             inside = [r for r in rows if r[0] <= t1 and r[3] > 0.5 * max(x[3] for x in rows)] if rows else []
             window = "warm-up + timed region (samples drawing > half of the maximum power)"
         if inside:
@@ -271,7 +327,16 @@ def run_ours(args):
                 return a, b, c
             return None
 
-        sampler = ClockSampler(local) if rank == 0 else None
+        sampler = None
+        if rank == 0:
+            bus = None
+            try:
+                pr = torch.cuda.get_device_properties(local)
+                bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            except Exception:
+                bus = None
+            sampler = ClockSampler(local, bus)
+            sampler.ready()
         for w in range(args.warmup):
             step(-1 - w, False)
         ctx.synchronize()
