@@ -157,18 +157,50 @@ mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, cons
     } else {
         chacha_draws8<ROUNDS>(key, u, blk);
     }
+    if constexpr (M61 && DK == DRAW_M61 && !FROM_MEM) {
+        // modulus 2^61 - 1, in-kernel draws: the arithmetic of the additive split's Mersenne path (above) -- a draw is
+        // (v & p) + (v >> 61) with no compare, secrets below 2^61 are taken as they are, and the sum is folded once.
+        // The two exceptions (a draw whose low 61 bits are within 8 of 2^61: 2^-29 per draw; a secret outside
+        // [0, 2^61)) are detected for the whole thread with a running maximum / a running OR and settled below.
+        constexpr uint32_t LOW29 = 0x1fffffffu;
+        uint32_t suspect = 0, wide = 0;
 #pragma unroll
-    for (int e = 0; e < G; e++) {
-        uint64_t s;
-        if (FROM_MEM) {
-            s = blk[e];
-        } else {
-            bool r;
-            s = draw_reduce<DK>(dr, blk[e], r);
-            rej |= r && e < nvalid;
+        for (int e = 0; e < G; e++) {
+            const uint64_t v = blk[e];
+            const uint32_t w0 = (uint32_t)(v >> 32), hi = w0 & LOW29;
+            const uint64_t sd = (((uint64_t)hi << 32) | (uint32_t)v) + (w0 >> 29);
+            suspect = max(suspect, hi);
+            wide |= (uint32_t)((uint64_t)x[e] >> 61);
+            const uint64_t t = (uint64_t)x[e] + sd;                    // < 2^62 when the secret is below 2^61
+            uint64_t r = (t & P61) + (t >> 61);                         // <= p
+            r = r >= P61 ? r - P61 : r;
+            mk[e] = (int64_t)sd;                                        // full.rs:24-27
+            md[e] = (int64_t)r;                                         // full.rs:28-31
         }
-        mk[e] = (int64_t)s;                                            // full.rs:24-27
-        md[e] = (int64_t)addmod(canon<M61>(f, x[e]), s, f.m);          // full.rs:28-31
+        if (suspect == LOW29 || wide != 0) {
+#pragma unroll
+            for (int e = 0; e < G; e++) {
+                bool r;
+                const uint64_t sd = draw_reduce<DK>(dr, blk[e], r);
+                rej |= r && e < nvalid;
+                mk[e] = (int64_t)sd;
+                md[e] = (int64_t)addmod(canon<M61>(f, x[e]), sd, f.m);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < G; e++) {
+            uint64_t s;
+            if (FROM_MEM) {
+                s = blk[e];
+            } else {
+                bool r;
+                s = draw_reduce<DK>(dr, blk[e], r);
+                rej |= r && e < nvalid;
+            }
+            mk[e] = (int64_t)s;                                            // full.rs:24-27
+            md[e] = (int64_t)addmod(canon<M61>(f, x[e]), s, f.m);          // full.rs:28-31
+        }
     }
     if (mask_out != nullptr) store_run<G>(mask_out + e0, mk, nvalid, lanes);
     store_run<G>(masked_out + e0, md, nvalid, lanes);
