@@ -111,7 +111,7 @@ uint64_t    sda_ctx_launch_count(const sda_ctx *ctx);
 const char *sda_ctx_last_kernel(const sda_ctx *ctx);
 /* pinned host memory for callers that want DMA-speed host entry points (optional).  With pinned input AND output
  * buffers sda_share_generate (tensor-core packed shapes) and sda_share_combine[_rows] / additive reconstruct / Full mask
- * combine walk vectors of 4 MB and more in 16 slices on three streams, so the copy in, the kernel and the copy out of
+ * combine walk vectors of 4 MB and more in 8 slices on three streams, so the copy in, the kernel and the copy out of
  * neighbouring slices overlap (PCIe is full duplex); results are identical, pageable buffers take the plain path. */
 int         sda_host_alloc(sda_ctx *ctx, size_t bytes, void **out);
 int         sda_host_free(sda_ctx *ctx, void *ptr);

@@ -418,7 +418,10 @@ int d2h(sda_ctx *ctx, void *dst, const void *src, size_t bytes) {
 // on the two copy engines and the SMs (pinned host buffers only; PCIe is full duplex) ------------------------
 constexpr size_t PIPE_MIN_BYTES = 4u << 20;    // below this a call is latency-bound and stays on one stream
 constexpr size_t PIPE_MAX_PITCH = 1u << 30;    // rows of the 2-D copies stay far below cudaDeviceProp::memPitch
-constexpr size_t PIPE_SLICES = 16;
+#ifndef SDA_PIPE_SLICES
+#define SDA_PIPE_SLICES 8       // measured: 8 slices 1.655e9, 16 1.60e9, 32 1.45e9, 64 1.33e9 secrets/s end to end
+#endif                          // (each slice costs ~35 us of submission; fewer slices leave more of the first copy in exposed)
+constexpr size_t PIPE_SLICES = SDA_PIPE_SLICES;
 
 int pipe_event(sda_ctx *ctx, size_t i, cudaEvent_t *out) {
     while (ctx->pipe_ev.size() <= i) {

@@ -216,9 +216,9 @@ def test_packed_tc_unit_walk_covers_every_slice_exactly_once():
 
 
 def test_host_slices_tile_the_vector():
-    """share_generate_sliced (csrc/api.cu): 16 slices, each a multiple of the kernel's pass size, cover [0, B)."""
+    """share_generate_sliced (csrc/api.cu): 8 slices, each a multiple of the kernel's pass size, cover [0, B)."""
     for dim in (524_288, 600_001, 10_000_000, 25_000_000, 3 * 512 * 8 * 5):
-        k, unit, slices = 3, 512, 16
+        k, unit, slices = 3, 512, 8
         B = (dim + k - 1) // k
         per = ((B + slices - 1) // slices + unit - 1) // unit * unit
         covered, b0 = 0, 0
