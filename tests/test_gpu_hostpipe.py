@@ -75,3 +75,20 @@ def test_share_combine_pinned_rows_and_matrix(ctx, oracle, modulus, P, L):
     # pageable inputs, pinned output and the other way round stay on the plain path
     assert np.array_equal(ctx.share_combine(s, m), want)
     assert np.array_equal(np.asarray(ctx.share_combine(s, [m[p] for p in range(P)], out=ctx.pinned_empty(L))), want)
+
+
+def test_share_combine_pinned_more_rows_than_one_staging_tile(ctx, oracle):
+    """the staging buffer holds 1 GB of rows: 300 rows of 4 MB take two row tiles, each walked in column slices,
+    the second accumulating onto the first (matrix and row-pointer forms)"""
+    P, L = 300, 524_288
+    s = LSS.Additive(3, P61)
+    rng = np.random.default_rng(300)
+    h_m = ctx.pinned_empty(P * L).reshape(P, L)
+    h_m[...] = rng.integers(0, P61, size=(P, L), dtype=np.int64)
+    h_m[7, ::3] = -5
+    want = util.canon(oracle, P61, oracle.share_combine(P61, np.asarray(h_m)))
+    out = ctx.pinned_empty(L)
+    out[...] = -1
+    assert np.array_equal(np.asarray(ctx.share_combine(s, h_m, out=out)), want)
+    out[...] = -1
+    assert np.array_equal(np.asarray(ctx.share_combine(s, [h_m[p] for p in range(P)], out=out)), want)
