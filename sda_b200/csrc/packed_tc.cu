@@ -14,7 +14,7 @@
 // 32 bytes of row computes D into TMEM; a thread then owns one batch (TMEM lane), reads its limb
 // sums with tcgen05.ld and only has to carry-propagate and reduce: ~16 integer instructions per share
 // instead of the 4 IMAD.WIDE per matrix entry + fold of the CUDA-core kernel (packed_m61.cu), whose
-// IMAD.WIDE stream is what bounds it (profiles/r01_k2.md).
+// IMAD.WIDE stream is what bounds it (profiles/r01_k2_cuda.md).
 //
 // The A rows are nothing but the operands as they lie in memory: a secret's 8 little-endian bytes
 // ARE its byte limbs, so the secrets go from global memory to the shared-memory tile unchanged, and
@@ -28,6 +28,17 @@
 // Randomness: every u64 comes from the participant's ChaCha keystream at its rand-0.3 stream
 // position exactly as in packed_m61.cu; a thread computes whole 64-byte blocks and scatters the
 // reduced draws into the rows they belong to.
+//
+// A pass of a persistent CTA (4 per SM) = G tiles of 128 batches of one participant:
+//   * its raw secrets (G x 128 x K x 8 bytes, contiguous in the vector) were brought into shared memory by one
+//     cp.async.bulk on the TMA unit, issued a pass earlier by one thread and completed on an mbarrier; each thread
+//     moves its row into the operand layout as 16-byte chunks (per-thread loads for ragged or unaligned passes);
+//   * its draws were staged, double-buffered, while the previous pass's MMAs ran;
+//   * the tiles go through the tensor core two at a time (two TMEM accumulators): one `full` wait, two
+//     tcgen05.ld groups, one `drained` arrive and one MMA issue per pair, the next pair's MMAs running under the
+//     compose arithmetic and the stores of the current one.
+// The kernel is bound by instruction issue (ChaCha20's 12 instructions per quarter round are 55 % of it), not by HBM,
+// latency or the MMA; profiles/r01_k2_variants.md records what was tried.
 #include <algorithm>
 #include <cstring>
 
