@@ -47,7 +47,8 @@ def workload_config(args, world):
         "dim": DIM, "participants_per_gpu_per_step": args.participants, "participants_total_config": 4096,
         "prime_modulus": (1 << 61) - 1, "omega_secrets": "order 7", "omega_shares": "order 11",
         "rng": f"ChaCha{args.rounds} keystream, rand-0.3 gen_range", "parallelism": f"participants sharded x{world}",
-        "share_gen_kernel": {"auto": "tcgen05 byte-limb GEMM", "tc": "tcgen05 byte-limb GEMM", "cuda": "IMAD.WIDE CUDA cores"}[args.packed_path],
+        "share_gen_kernel": {"auto": "tcgen05 byte-limb GEMM, paired tiles", "tc": "tcgen05 byte-limb GEMM, paired tiles",
+                             "tc1": "tcgen05 byte-limb GEMM, first generation", "cuda": "IMAD.WIDE CUDA cores"}[args.packed_path],
         "l2": "inputs (>= 10 GB per step) far exceed the 126 MB L2; no flush needed",
     }
 
@@ -289,7 +290,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     ctx = sda_b200.Context(local, rng_rounds=args.rounds)
-    ctx.set_packed_path({"auto": 0, "cuda": 1, "tc": 2}[args.packed_path])
+    ctx.set_packed_path({"auto": 0, "cuda": 1, "tc": 2, "tc1": 3}[args.packed_path])
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     scheme = params.config3()
@@ -563,8 +564,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--participants", type=int, default=256, help="resident participants per GPU per step")
     ap.add_argument("--rounds", type=int, default=20, choices=[8, 12, 20], help="ChaCha rounds of the sharing randomness")
-    ap.add_argument("--packed-path", default="auto", choices=["auto", "cuda", "tc"],
-                    help="share-gen kernel: tcgen05 byte-limb GEMM (auto/tc) or the IMAD.WIDE CUDA-core kernel")
+    ap.add_argument("--packed-path", default="auto", choices=["auto", "cuda", "tc", "tc1"],
+                    help="share-gen kernel: tcgen05 byte-limb GEMM (auto/tc: paired tiles, tc1: first generation) or the "
+                         "IMAD.WIDE CUDA-core kernel")
     ap.add_argument("--e2e-participants", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -61,7 +61,7 @@ enum {
     SDA_OK = 0,
     SDA_ERR_INVALID = 1,     /* the reference returns Err(..) or panics on this input */
     SDA_ERR_CUDA = 2,        /* CUDA runtime / driver failure (incl. no device) */
-    SDA_ERR_NCCL = 3,        /* reserved: collectives are driven by the host layer */
+    SDA_ERR_NCCL = 3,        /* NCCL failure (incl. libnccl.so.2 not loadable) in a multi-GPU entry point */
     SDA_ERR_UNSUPPORTED = 4  /* parameters outside what the kernels implement */
 };
 
@@ -98,8 +98,11 @@ int         sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds);
 int         sda_ctx_get_rng_rounds(const sda_ctx *ctx);
 /* Which kernels evaluate the packed-Shamir maps over 2^61-1 (share generation for the instantiated
  * shapes, reconstruction for k, m' <= 16): the tcgen05 (tensor-core, byte-limb GEMM) ones or the
- * CUDA-core ones.  Both are exact and produce identical results; AUTO picks the tensor-core kernels. */
-enum { SDA_PACKED_PATH_AUTO = 0, SDA_PACKED_PATH_CUDA_CORES = 1, SDA_PACKED_PATH_TENSOR_CORES = 2 };
+ * CUDA-core ones.  All are exact and produce identical results; AUTO picks the tensor-core kernels.
+ * TENSOR_CORES_V1 keeps share generation on the first-generation tensor-core kernel (one batch per thread
+ * and tile) instead of the paired-tile one, for side-by-side measurements. */
+enum { SDA_PACKED_PATH_AUTO = 0, SDA_PACKED_PATH_CUDA_CORES = 1, SDA_PACKED_PATH_TENSOR_CORES = 2,
+       SDA_PACKED_PATH_TENSOR_CORES_V1 = 3 };
 int         sda_ctx_set_packed_path(sda_ctx *ctx, int path);
 /* stream (cudaStream_t) the *_dev entry points launch on; default: a context-owned stream */
 int         sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream);
@@ -209,6 +212,45 @@ int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_
                          size_t mask_len, int64_t *d_out);
 int sda_unmask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_mask, const int64_t *d_masked,
                    size_t dim, int64_t *d_out);
+
+/* ---- multi-GPU clerk sum --------------------------------------------------------------------- */
+/* The one step of the path with an exchange (ShareCombiner::combine, combiner.rs:15-29, called at clerk.rs:85-86):
+ * the participants' rows are sharded over the GPUs of a box, every GPU sums its rows, and the canonical partial sums
+ * are added over NVLink by ONE NCCL collective inside the library (ncclReduce of u64 + one mod pass on the root while
+ * ranks * modulus <= 2^64, e.g. 8 GPUs at a 61-bit modulus; otherwise ncclAllGather + the modular combine kernel).
+ * NCCL is bound at run time (dlopen of libnccl.so.2, the process's copy if it has one); hosts that never call these
+ * entry points do not need it.  Two forms:
+ *
+ * (1) one process per GPU (what bench.py --gpus N and an MPI-style host use): rank 0 calls sda_nccl_unique_id, the
+ *     host application hands the 128 bytes to the other ranks, every rank calls sda_ctx_comm_init_rank on its own
+ *     context (collective), then sda_share_combine_ranks_dev / sda_partial_sums_reduce_dev (collective, in the same
+ *     order on every rank, launched on each context's stream). */
+#define SDA_NCCL_UNIQUE_ID_BYTES 128
+int sda_nccl_unique_id(uint8_t id_out[SDA_NCCL_UNIQUE_ID_BYTES]);
+int sda_ctx_comm_init_rank(sda_ctx *ctx, const uint8_t id[SDA_NCCL_UNIQUE_ID_BYTES], int nranks, int rank);
+int sda_ctx_comm_rank(const sda_ctx *ctx);
+int sda_ctx_comm_size(const sda_ctx *ctx);   /* 1 without a communicator */
+/* d_partials[count]: this rank's canonical column sums, in place; afterwards the root's buffer holds the sums over
+ * all ranks mod `modulus` (canonical), the other ranks' buffers are unspecified.  No-op for a single rank. */
+int sda_partial_sums_reduce_dev(sda_ctx *ctx, int64_t modulus, int64_t *d_partials, size_t count, int root);
+/* sda_share_combine_dev on this rank's rows (P_local may be 0), then the exchange: root's d_out = the clerk sum
+ * over every rank's rows. */
+int sda_share_combine_ranks_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld,
+                                size_t P_local, size_t L, const int64_t *d_acc_in, int64_t *d_out, int root);
+/* (2) one process, several GPUs (what a Rust clerk binds: no launcher, no torch): the returned context is member 0
+ *     (device devices[0]) and owns one member context per further device plus the communicator; every single-GPU
+ *     entry point keeps working on it (on device devices[0]).  sda_ctx_destroy releases all of it. */
+int sda_ctx_create_multi(const int *devices, int ndev, sda_ctx **out);
+int      sda_ctx_multi_count(const sda_ctx *ctx);          /* 1 for a plain context */
+sda_ctx *sda_ctx_multi_member(sda_ctx *ctx, int i);        /* member i's context (its device, its stream) */
+/* rows resident on the devices: d_shares[i] = member i's [P_per_device[i]][ld] block (device i memory),
+ * d_partials[i] = L elements of scratch on device i (i >= 1; entry 0 unused), d_out = L elements on device 0. */
+int sda_share_combine_multi_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *d_shares, size_t ld,
+                                const size_t *P_per_device, size_t L, int64_t *const *d_partials, int64_t *d_out);
+/* ShareCombiner::combine on `&Vec<Vec<Share>>` host rows (sda_share_combine_rows' contract): contiguous blocks of
+ * participants go to the devices over their own PCIe links (one host thread per device), then the exchange. */
+int sda_share_combine_rows_multi(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *rows,
+                                 const size_t *row_lens, size_t P, int64_t *out, size_t *out_len);
 
 /* ---- share wire codec: the step either side of the path ------------------------------------ */
 /* ShareEncryptor::encrypt's encoding loop (client/src/crypto/encryption/sodium.rs:35-41) and

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("SDA_B200_LIB") or os.path.join(_HERE, "libsda_b200.so
 SDA_OK, SDA_ERR_INVALID, SDA_ERR_CUDA, SDA_ERR_NCCL, SDA_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 SHARING_ADDITIVE, SHARING_PACKED_SHAMIR = 0, 1
 MASK_NONE, MASK_FULL, MASK_CHACHA = 0, 1, 2
-PACKED_PATH_AUTO, PACKED_PATH_CUDA_CORES, PACKED_PATH_TENSOR_CORES = 0, 1, 2
+PACKED_PATH_AUTO, PACKED_PATH_CUDA_CORES, PACKED_PATH_TENSOR_CORES, PACKED_PATH_TENSOR_CORES_V1 = 0, 1, 2, 3
 
 
 class sda_sharing_scheme(C.Structure):
@@ -73,6 +73,17 @@ PROTOTYPES = {
     "sda_mask_dev": (_int, [_vp, _ms, _vp, _sz, _vp, _vp, _vp]),
     "sda_mask_combine_dev": (_int, [_vp, _ms, _vp, _sz, _sz, _vp]),
     "sda_unmask_dev": (_int, [_vp, _ms, _vp, _vp, _sz, _vp]),
+    "sda_nccl_unique_id": (_int, [_vp]),
+    "sda_ctx_comm_init_rank": (_int, [_vp, _vp, _int, _int]),
+    "sda_ctx_comm_rank": (_int, [_vp]),
+    "sda_ctx_comm_size": (_int, [_vp]),
+    "sda_partial_sums_reduce_dev": (_int, [_vp, _i64, _vp, _sz, _int]),
+    "sda_share_combine_ranks_dev": (_int, [_vp, _ss, _vp, _sz, _sz, _sz, _vp, _vp, _int]),
+    "sda_ctx_create_multi": (_int, [C.POINTER(_int), _int, C.POINTER(_vp)]),
+    "sda_ctx_multi_count": (_int, [_vp]),
+    "sda_ctx_multi_member": (_vp, [_vp, _int]),
+    "sda_share_combine_multi_dev": (_int, [_vp, _ss, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "sda_share_combine_rows_multi": (_int, [_vp, _ss, _vp, _vp, _sz, _vp, _psz]),
     "sda_varint_max_bytes": (_sz, [_sz]),
     "sda_varint_encode": (_int, [_vp, _vp, _sz, _vp, _psz]),
     "sda_varint_decode": (_int, [_vp, _vp, _sz, _vp, _sz, _psz]),

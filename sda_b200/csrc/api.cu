@@ -4,12 +4,16 @@
 // implementation of any hot-path function in this file: every entry point ends in kernel
 // launches and fails with SDA_ERR_CUDA when there is no device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sda_b200.h"
@@ -79,9 +83,10 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image, tc_image_r;
+    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image, tc_image_r, tc2_image;
     int packed_path = SDA_PACKED_PATH_AUTO;
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
+    std::vector<uint64_t> tc2_image_key;  // likewise for the paired-tile kernel's two images (packed_tc2.cu)
     std::vector<uint64_t> tc_image_r_key; // (k, m', R) likewise for the reconstruction operand
     std::vector<uint64_t> r_key;          // (scheme, clerk subset) of r_cached
     Matrix r_cached;
@@ -90,6 +95,11 @@ struct sda_ctx {
     unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
     unsigned *h_flag = nullptr;    // pinned mirror
     PinBuf stage[2];               // pinned staging for pageable host buffers
+    // multi-GPU: the NCCL communicator this context is a rank of, and -- for the one-process form
+    // (sda_ctx_create_multi) -- the member contexts of the other devices, owned by member 0
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    std::vector<sda_ctx *> members;   // [0] = this context when non-empty
     LaunchCtx lc() { return LaunchCtx{stream, &nlaunch, sm_count, &kernel_name}; }
 };
 
@@ -458,6 +468,41 @@ int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
     return SDA_OK;
 }
 
+// Tensor-core share generation, whichever kernel serves the scheme: the paired-tile kernel (packed_tc2.cu) for
+// 2^61 - 1 when the vector fits its 32-bit row offsets, packed_tc.cu otherwise (any prime; or when the context asks
+// for it with SDA_PACKED_PATH_TENSOR_CORES_V1).  Both generate batches first_batch .. first_batch + n_batches - 1 of
+// every participant; first_batch is a multiple of share_tc_slice_batches().
+bool use_tc2(const sda_ctx *ctx, const Packed &pk, size_t dim) {
+    return pk.p == P61 && ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 && packed_share_tc2_supported(pk.k, pk.t, pk.n, dim);
+}
+size_t share_tc_slice_batches(const sda_ctx *ctx, const Packed &pk, size_t dim) {
+    return use_tc2(ctx, pk, dim) ? packed_share_tc2_slice_batches(pk.k, pk.t, pk.n) : packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
+}
+int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const FieldParams &f, const DrawParams &dr,
+                    const int64_t *d_secrets, size_t ld, size_t P, size_t dim, size_t first_batch, size_t n_batches,
+                    const ChaChaKey *d_keys, int64_t *d_out) {
+    if (!use_tc2(ctx, pk, dim)) {
+        OK(ensure_tc_image(ctx, pk, M));
+        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches,
+                                  d_keys, (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
+        return SDA_OK;
+    }
+    const size_t ib = packed_share_tc2_image_bytes(pk.k, pk.t, pk.n);
+    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
+    key.insert(key.end(), M.e, M.e + M.rows * M.cols);
+    if (key != ctx->tc2_image_key) {
+        std::vector<uint8_t> img(ib);
+        packed_share_tc2_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
+        CU(ctx->tc2_image.reserve(ib));
+        CU(cudaMemcpyAsync(ctx->tc2_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
+        ctx->tc2_image_key = key;
+    }
+    CU(launch_packed_share_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
+                               (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
+    return SDA_OK;
+}
+
 // ---- core device-side operations (shared by host and device entry points) --------------------
 
 int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t ld, size_t P,
@@ -491,10 +536,8 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     const bool use_tc = !additive && fast && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
                         packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0;
     if (use_tc) {
-        OK(ensure_tc_image(ctx, pk, M));
         OK(clear_flags(ctx));
-        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, 0, B, d_keys,
-                                  (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
+        OK(launch_share_tc(ctx, pk, M, f, dr, d_secrets, ld, P, dim, 0, B, d_keys, d_out));
         unsigned rejected = 0;
         OK(read_flags(ctx, &rejected, nullptr));
         exact = rejected != 0;
@@ -691,6 +734,115 @@ int chacha_mask_combine_core(sda_ctx *ctx, const sda_masking_scheme *s, const in
 
 // =================================================================================================
 #pragma GCC visibility push(default)
+
+namespace {
+
+// ---- NCCL, bound at run time -----------------------------------------------------------------------------
+// The library takes libnccl.so.2 from the process (dlopen by soname: a host application that already has NCCL
+// loaded -- torch does -- shares its copy) instead of linking it, so hosts that never call the multi-GPU entry
+// points do not need NCCL installed.  SDA_B200_NCCL_LIB overrides the name.
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+};
+
+const NcclApi *nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("SDA_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *nm : names) {
+            if (!nm || !*nm) continue;
+            api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (api.handle) break;
+            api.error = dlerror();
+        }
+        if (!api.handle) return;
+        bool ok = true;
+        auto bind = [&](auto &fn, const char *sym) {
+            fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(dlsym(api.handle, sym));
+            if (!fn) {
+                ok = false;
+                api.error = std::string("missing symbol ") + sym;
+            }
+        };
+        bind(api.GetVersion, "ncclGetVersion");
+        bind(api.GetUniqueId, "ncclGetUniqueId");
+        bind(api.CommInitRank, "ncclCommInitRank");
+        bind(api.CommInitAll, "ncclCommInitAll");
+        bind(api.CommDestroy, "ncclCommDestroy");
+        bind(api.Reduce, "ncclReduce");
+        bind(api.AllGather, "ncclAllGather");
+        bind(api.GroupStart, "ncclGroupStart");
+        bind(api.GroupEnd, "ncclGroupEnd");
+        bind(api.GetErrorString, "ncclGetErrorString");
+        if (!ok) {
+            dlclose(api.handle);
+            api.handle = nullptr;
+        }
+    });
+    return &api;
+}
+
+#define NC(call)                                                                                              \
+    do {                                                                                                      \
+        ncclResult_t r_ = (call);                                                                             \
+        if (r_ != ncclSuccess)                                                                                \
+            return fail(ctx, SDA_ERR_NCCL, "NCCL error %s at %s:%d", nccl_api()->GetErrorString(r_), __FILE__, __LINE__); \
+    } while (0)
+
+int need_nccl(sda_ctx *ctx, const NcclApi **out) {
+    const NcclApi *api = nccl_api();
+    if (!api->handle) return fail(ctx, SDA_ERR_NCCL, "libnccl.so.2 could not be loaded: %s", api->error.c_str());
+    *out = api;
+    return SDA_OK;
+}
+
+void comm_release(sda_ctx *ctx) {
+    if (ctx->comm && nccl_api()->handle) nccl_api()->CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+    ctx->comm_rank = 0;
+    ctx->comm_size = 1;
+}
+
+// One rank's part of the clerk-sum exchange: d_partials holds `count` canonical residues (this rank's
+// column sums); on return the root's buffer holds the sums over all ranks mod m, canonical.  While comm_size * m
+// fits 64 bits the exchange is one ncclReduce(sum) of u64 followed by one mod pass on the root; otherwise the
+// partials are gathered and folded by the combine kernel, which adds mod m.  Call inside ncclGroupStart/End when
+// several ranks live in this process (group = true defers nothing here: NCCL queues the collective).
+int reduce_partials_enqueue(sda_ctx *ctx, const NcclApi *api, const FieldParams &f, int64_t *d_partials, size_t count, int root,
+                            bool *needs_fold) {
+    const bool sum_fits = (u128)f.m * (u128)ctx->comm_size <= ((u128)1 << 64);
+    *needs_fold = !sum_fits;
+    if (sum_fits) {
+        NC(api->Reduce(d_partials, d_partials, count, ncclUint64, ncclSum, root, ctx->comm, ctx->stream));
+        return SDA_OK;
+    }
+    CU(ctx->aux.reserve((size_t)ctx->comm_size * count * sizeof(int64_t)));
+    NC(api->AllGather(d_partials, ctx->aux.p, count, ncclUint64, ctx->comm, ctx->stream));
+    return SDA_OK;
+}
+int reduce_partials_finish(sda_ctx *ctx, const FieldParams &f, int64_t *d_partials, size_t count, int root, bool needs_fold) {
+    if (ctx->comm_rank != root) return SDA_OK;
+    if (!needs_fold) {
+        CU(launch_mod_reduce(ctx->lc(), f, d_partials, count, d_partials, true));
+        return SDA_OK;
+    }
+    return combine_core(ctx, (int64_t)f.m, (const int64_t *)ctx->aux.p, count, (size_t)ctx->comm_size, count, nullptr, d_partials);
+}
+
+}  // namespace
+
 extern "C" {
 
 int sda_abi_version(void) { return SDA_B200_ABI_VERSION; }
@@ -735,9 +887,12 @@ int sda_ctx_create(int device, sda_ctx **out) {
 
 void sda_ctx_destroy(sda_ctx *ctx) {
     if (!ctx) return;
+    for (size_t i = 1; i < ctx->members.size(); i++) sda_ctx_destroy(ctx->members[i]);
+    ctx->members.clear();
     DeviceGuard g(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r}) b->release();
+    comm_release(ctx);
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -762,7 +917,8 @@ int sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds) {
 int sda_ctx_get_rng_rounds(const sda_ctx *ctx) { return ctx ? ctx->rounds : 0; }
 int sda_ctx_set_packed_path(sda_ctx *ctx, int path) {
     if (!ctx) return SDA_ERR_INVALID;
-    if (path != SDA_PACKED_PATH_AUTO && path != SDA_PACKED_PATH_CUDA_CORES && path != SDA_PACKED_PATH_TENSOR_CORES)
+    if (path != SDA_PACKED_PATH_AUTO && path != SDA_PACKED_PATH_CUDA_CORES && path != SDA_PACKED_PATH_TENSOR_CORES &&
+        path != SDA_PACKED_PATH_TENSOR_CORES_V1)
         return fail(ctx, SDA_ERR_INVALID, "unknown packed-share path %d", path);
     ctx->packed_path = path;
     return SDA_OK;
@@ -1101,7 +1257,7 @@ static int share_generate_sliced(sda_ctx *ctx, const sda_sharing_scheme *s, cons
     OK(validate(ctx, s, &pk));
     if (s->kind != SDA_SHARING_PACKED_SHAMIR || ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES || s->modulus < 3 || !seed)
         return SDA_OK;
-    const size_t slice_unit = packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
+    const size_t slice_unit = share_tc_slice_batches(ctx, pk, dim);
     if (slice_unit == 0 || dim * sizeof(int64_t) < PIPE_MIN_BYTES || dim * sizeof(int64_t) > PIPE_MAX_PITCH ||
         !is_pinned(secrets) || !is_pinned(shares_out))
         return SDA_OK;
@@ -1111,7 +1267,6 @@ static int share_generate_sliced(sda_ctx *ctx, const sda_sharing_scheme *s, cons
     const DrawParams dr = make_draw((uint64_t)s->modulus - 1);
     Matrix M;
     OK(share_matrix_cached(ctx, pk, &M));
-    OK(ensure_tc_image(ctx, pk, M));
     OK(upload_keys(ctx, seed, 1));
     OK(clear_flags(ctx));
     OK(pipe_begin(ctx));
@@ -1127,8 +1282,7 @@ static int share_generate_sliced(sda_ctx *ctx, const sda_sharing_scheme *s, cons
         CU(cudaMemcpyAsync((void *)(d_in + e0), secrets + e0, (e1 - e0) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->h2d_stream));
         CU(cudaEventRecord(in_ready, ctx->h2d_stream));
         CU(cudaStreamWaitEvent(ctx->stream, in_ready, 0));
-        CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_in, ldp, 1, dim, b0, nb,
-                                  (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
+        OK(launch_share_tc(ctx, pk, M, f, dr, d_in, ldp, 1, dim, b0, nb, (const ChaChaKey *)ctx->keys.p, d_out));
         CU(cudaEventRecord(out_ready, ctx->stream));
         CU(cudaStreamWaitEvent(ctx->d2h_stream, out_ready, 0));
         CU(cudaMemcpy2DAsync(shares_out + b0, B * sizeof(int64_t), d_out + b0, B * sizeof(int64_t), nb * sizeof(int64_t), n,
@@ -1173,7 +1327,8 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
     if (P == 0) CU(cudaMemsetAsync(d_acc, 0, row_bytes, ctx->stream));
     // pinned rows: walk the columns in slices so that the rows of slice i + 1 arrive while slice i is summed and
     // the sums of slice i - 1 leave (the kernel takes any column range of the staged matrix: row stride ldp)
-    bool pinned = P > 0 && L * sizeof(int64_t) >= PIPE_MIN_BYTES && L * sizeof(int64_t) <= PIPE_MAX_PITCH && is_pinned(out);
+    // out == nullptr: the sum stays on the device (ctx->out), for the multi-GPU entry points
+    bool pinned = P > 0 && L * sizeof(int64_t) >= PIPE_MIN_BYTES && L * sizeof(int64_t) <= PIPE_MAX_PITCH && (!out || is_pinned(out));
     if (pinned && shares) pinned = is_pinned(shares);
     for (size_t p = 0; pinned && !shares && p < P; p++) pinned = is_pinned(rows[p]);
     if (pinned) {
@@ -1204,7 +1359,7 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
                 CU(cudaStreamWaitEvent(ctx->stream, in_ready, 0));
                 OK(combine_core(ctx, modulus, d_in + c0, ldp, pc, nc, p0 ? d_acc + c0 : nullptr, d_acc + c0));
                 CU(cudaEventRecord(summed, ctx->stream));
-                if (last) {
+                if (last && out) {
                     CU(cudaStreamWaitEvent(ctx->d2h_stream, summed, 0));
                     CU(cudaMemcpyAsync(out + c0, d_acc + c0, nc * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->d2h_stream));
                 }
@@ -1226,6 +1381,10 @@ static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, co
                 OK(h2d(ctx, d_in + p * ldp, shares ? shares + (p0 + p) * L : rows[p0 + p], L * sizeof(int64_t)));
         }
         OK(combine_core(ctx, modulus, d_in, ldp, pc, L, p0 ? d_acc : nullptr, d_acc));
+    }
+    if (!out) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        return SDA_OK;
     }
     return d2h(ctx, out, d_acc, L * sizeof(int64_t));
 }
@@ -1376,6 +1535,213 @@ int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, s
     CU(launch_submod(ctx->lc(), make_field((uint64_t)s->modulus), (const int64_t *)ctx->in.p, (const int64_t *)ctx->aux.p,
                      dim, (int64_t *)ctx->out.p));
     return d2h(ctx, out, ctx->out.p, bytes);
+}
+
+// ---- multi-GPU clerk sum (clerk.rs:85-86 when one box holds several GPUs) ------------------------------
+
+int sda_nccl_unique_id(uint8_t id_out[SDA_NCCL_UNIQUE_ID_BYTES]) {
+    sda_ctx *ctx = nullptr;
+    if (!id_out) return fail(ctx, SDA_ERR_INVALID, "null id buffer");
+    const NcclApi *api;
+    OK(need_nccl(ctx, &api));
+    static_assert(sizeof(ncclUniqueId) == SDA_NCCL_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NC(api->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return SDA_OK;
+}
+
+int sda_ctx_comm_init_rank(sda_ctx *ctx, const uint8_t id[SDA_NCCL_UNIQUE_ID_BYTES], int nranks, int rank) {
+    if (!ctx) return SDA_ERR_INVALID;
+    if (!id || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, SDA_ERR_INVALID, "bad communicator arguments");
+    if (!ctx->members.empty()) return fail(ctx, SDA_ERR_INVALID, "context already belongs to a one-process device group");
+    const NcclApi *api;
+    OK(need_nccl(ctx, &api));
+    DeviceGuard g(ctx->device);
+    comm_release(ctx);
+    ncclUniqueId nid;
+    memcpy(&nid, id, sizeof nid);
+    NC(api->CommInitRank(&ctx->comm, nranks, nid, rank));
+    ctx->comm_rank = rank;
+    ctx->comm_size = nranks;
+    return SDA_OK;
+}
+
+int sda_ctx_comm_rank(const sda_ctx *ctx) { return ctx ? ctx->comm_rank : -1; }
+int sda_ctx_comm_size(const sda_ctx *ctx) { return ctx ? ctx->comm_size : 0; }
+
+int sda_partial_sums_reduce_dev(sda_ctx *ctx, int64_t modulus, int64_t *d_partials, size_t count, int root) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
+    if (root < 0 || root >= ctx->comm_size) return fail(ctx, SDA_ERR_INVALID, "root %d outside the communicator", root);
+    if (count == 0) return SDA_OK;
+    if (!ctx->members.empty()) return fail(ctx, SDA_ERR_INVALID, "one-process device groups reduce through sda_share_combine_multi*");
+    if (ctx->comm_size == 1) return SDA_OK;   // a single rank's canonical partial sums are the result
+    if (!ctx->comm) return fail(ctx, SDA_ERR_INVALID, "no communicator: call sda_ctx_comm_init_rank first");
+    const NcclApi *api;
+    OK(need_nccl(ctx, &api));
+    const FieldParams f = make_field((uint64_t)modulus);
+    bool fold = false;
+    OK(reduce_partials_enqueue(ctx, api, f, d_partials, count, root, &fold));
+    return reduce_partials_finish(ctx, f, d_partials, count, root, fold);
+}
+
+int sda_share_combine_ranks_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld, size_t P_local,
+                                size_t L, const int64_t *d_acc_in, int64_t *d_out, int root) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(validate(ctx, s, nullptr));
+    if (ld < L) return fail(ctx, SDA_ERR_INVALID, "Wrong dimension");
+    if (L == 0) return SDA_OK;
+    if (P_local == 0 && !d_acc_in) CU(cudaMemsetAsync(d_out, 0, L * sizeof(int64_t), ctx->stream));   // a rank without rows adds 0
+    else OK(combine_core(ctx, s->modulus, d_shares, ld, P_local, L, d_acc_in, d_out));
+    return sda_partial_sums_reduce_dev(ctx, s->modulus, d_out, L, root);
+}
+
+int sda_ctx_create_multi(const int *devices, int ndev, sda_ctx **out) {
+    sda_ctx *ctx = nullptr;
+    if (!out) return SDA_ERR_INVALID;
+    *out = nullptr;
+    if (!devices || ndev < 1) return fail(ctx, SDA_ERR_INVALID, "need at least one device");
+    for (int i = 0; i < ndev; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(ctx, SDA_ERR_INVALID, "device %d listed twice", devices[i]);
+    std::vector<sda_ctx *> m((size_t)ndev, nullptr);
+    auto undo = [&]() {
+        for (int i = ndev - 1; i >= 0; i--)
+            if (m[i]) {
+                m[i]->members.clear();
+                sda_ctx_destroy(m[i]);
+            }
+    };
+    for (int i = 0; i < ndev; i++) {
+        const int rc = sda_ctx_create(devices[i], &m[i]);
+        if (rc != SDA_OK) {
+            undo();
+            return rc;   // message already in the thread's create error
+        }
+    }
+    if (ndev > 1) {
+        const NcclApi *api = nccl_api();
+        std::vector<ncclComm_t> comms((size_t)ndev, nullptr);
+        ncclResult_t r = api->handle ? api->CommInitAll(comms.data(), ndev, devices) : ncclSystemError;
+        if (r != ncclSuccess) {
+            const std::string why = api->handle ? api->GetErrorString(r) : "libnccl.so.2 could not be loaded: " + api->error;
+            undo();
+            return fail(ctx, SDA_ERR_NCCL, "NCCL communicator over %d devices: %s", ndev, why.c_str());
+        }
+        for (int i = 0; i < ndev; i++) {
+            m[i]->comm = comms[i];
+            m[i]->comm_rank = i;
+            m[i]->comm_size = ndev;
+        }
+    }
+    m[0]->members = m;
+    *out = m[0];
+    return SDA_OK;
+}
+
+int sda_ctx_multi_count(const sda_ctx *ctx) { return ctx ? (ctx->members.empty() ? 1 : (int)ctx->members.size()) : 0; }
+sda_ctx *sda_ctx_multi_member(sda_ctx *ctx, int i) {
+    if (!ctx) return nullptr;
+    if (ctx->members.empty()) return i == 0 ? ctx : nullptr;
+    return i >= 0 && i < (int)ctx->members.size() ? ctx->members[(size_t)i] : nullptr;
+}
+
+// member i's canonical partial sums (d_part[i], `count` elements on device i) -> totals mod m in d_part[0]
+static int multi_reduce(sda_ctx *ctx, int64_t modulus, const std::vector<int64_t *> &d_part, size_t count) {
+    const size_t G = ctx->members.size();
+    if (G <= 1) return SDA_OK;
+    const NcclApi *api;
+    OK(need_nccl(ctx, &api));
+    const FieldParams f = make_field((uint64_t)modulus);
+    std::vector<char> fold(G, 0);
+    NC(api->GroupStart());
+    int rc = SDA_OK;
+    for (size_t i = 0; i < G && rc == SDA_OK; i++) {
+        sda_ctx *mi = ctx->members[i];
+        DeviceGuard g(mi->device);
+        bool fl = false;
+        rc = reduce_partials_enqueue(mi, api, f, d_part[i], count, 0, &fl);
+        fold[i] = fl;
+        if (rc != SDA_OK && mi != ctx) ctx->err = mi->err;
+    }
+    NC(api->GroupEnd());
+    OK(rc);
+    DeviceGuard g(ctx->device);
+    OK(reduce_partials_finish(ctx, f, d_part[0], count, 0, fold[0] != 0));
+    for (size_t i = 1; i < G; i++) {       // the members' streams have nothing left but the collective
+        DeviceGuard gi(ctx->members[i]->device);
+        CU(cudaStreamSynchronize(ctx->members[i]->stream));
+    }
+    return SDA_OK;
+}
+
+int sda_share_combine_multi_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *d_shares, size_t ld,
+                                const size_t *P_per_device, size_t L, int64_t *const *d_partials, int64_t *d_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    OK(validate(ctx, s, nullptr));
+    if (!d_shares || !P_per_device || !d_partials || !d_out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    if (ld < L) return fail(ctx, SDA_ERR_INVALID, "Wrong dimension");
+    if (L == 0) return SDA_OK;
+    const size_t G = (size_t)sda_ctx_multi_count(ctx);
+    std::vector<int64_t *> part(G);
+    for (size_t i = 0; i < G; i++) {
+        sda_ctx *mi = sda_ctx_multi_member(ctx, (int)i);
+        DeviceGuard g(mi->device);
+        part[i] = i == 0 ? d_out : d_partials[i];
+        int rc = SDA_OK;
+        if (P_per_device[i] == 0) {
+            if (cudaMemsetAsync(part[i], 0, L * sizeof(int64_t), mi->stream) != cudaSuccess) rc = fail(mi, SDA_ERR_CUDA, "cudaMemsetAsync failed");
+        } else {
+            rc = combine_core(mi, s->modulus, d_shares[i], ld, P_per_device[i], L, nullptr, part[i]);
+        }
+        if (rc != SDA_OK) {
+            if (mi != ctx) ctx->err = mi->err;
+            return rc;
+        }
+    }
+    return multi_reduce(ctx, s->modulus, part, L);
+}
+
+int sda_share_combine_rows_multi(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *const *rows, const size_t *row_lens,
+                                 size_t P, int64_t *out, size_t *out_len) {
+    if (!ctx) return SDA_ERR_INVALID;
+    OK(validate(ctx, s, nullptr));
+    const size_t L = P ? row_lens[0] : 0;   // combiner.rs:17
+    if (out_len) *out_len = L;
+    for (size_t p = 0; p < P; p++)
+        if (row_lens[p] != L) return fail(ctx, SDA_ERR_INVALID, "Wrong dimension");   // combiner.rs:21
+    if (L == 0) return SDA_OK;
+    if (!rows || !out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    const size_t G = (size_t)sda_ctx_multi_count(ctx);
+    // contiguous blocks of participants per device, each summed by its own context on its own host thread
+    // (every device has its own PCIe link; one context per thread is the library's concurrency model)
+    std::vector<int> rcs(G, SDA_OK);
+    std::vector<std::thread> th;
+    const size_t per = (P + G - 1) / G;
+    for (size_t i = 0; i < G; i++) {
+        th.emplace_back([&, i]() {
+            sda_ctx *mi = sda_ctx_multi_member(ctx, (int)i);
+            const size_t p0 = std::min(P, i * per), pc = std::min(per, P - p0);
+            cudaSetDevice(mi->device);
+            rcs[i] = combine_host(mi, s->modulus, nullptr, rows + p0, pc, L, nullptr);   // sum stays in mi->out
+        });
+    }
+    for (auto &t : th) t.join();
+    std::vector<int64_t *> part(G);
+    for (size_t i = 0; i < G; i++) {
+        sda_ctx *mi = sda_ctx_multi_member(ctx, (int)i);
+        if (rcs[i] != SDA_OK) {
+            if (mi != ctx) ctx->err = mi->err;
+            return rcs[i];
+        }
+        part[i] = (int64_t *)mi->out.p;
+    }
+    OK(multi_reduce(ctx, s->modulus, part, L));
+    DeviceGuard g(ctx->device);
+    return d2h(ctx, out, part[0], L * sizeof(int64_t));
 }
 
 }  // extern "C"

@@ -94,6 +94,16 @@ cudaError_t launch_packed_share_tc(const LaunchCtx &lc, const FieldParams &f, co
                                    int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
                                    size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *shares_out,
                                    unsigned *flag);
+// the paired-tile generation of the same kernel (packed_tc2.cu): 2^61 - 1 only, same slicing contract; two operand
+// images (image_bytes covers both).  `supported` also bounds the vector so that a participant's n share rows stay
+// within 32-bit byte offsets.
+bool packed_share_tc2_supported(int k, int t, int n, size_t dim);
+size_t packed_share_tc2_image_bytes(int k, int t, int n);
+void packed_share_tc2_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img);
+size_t packed_share_tc2_slice_batches(int k, int t, int n);
+cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
+                                    size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
+                                    const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
 // fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,

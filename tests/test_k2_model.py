@@ -228,3 +228,138 @@ def test_host_slices_tile_the_vector():
             covered += nb
             b0 += per
         assert covered == B and (B + per - 1) // per <= slices
+
+
+# ---- packed_tc2.cu: uneven limb plan, one wide term, paired tiles -----------------------------------
+LOW29 = (1 << 29) - 1
+
+
+def limb_plan2(kt):
+    """Shape2::W5 / limb_plan(): widths (8,8,8,8,8,W5,8,13-W5), W5 the widest with e2 = d4 + 256 d5 < 2^29"""
+    w5 = next(w for w in range(8, 4, -1) if 8 * kt * 255 * (255 + ((1 << w) - 1) * 256) < (1 << 29))
+    return [8, 8, 8, 8, 8, w5, 8, 13 - w5], [0, 8, 16, 24, 32, 40, 40 + w5, 48 + w5]
+
+
+def compose2(d, w, kt):
+    """compose2<W5> of packed_tc2.cu, word for word; every intermediate asserted to fit its register"""
+    w5 = w[5]
+    for s in range(8):
+        assert 0 <= d[s] <= 8 * kt * 255 * ((1 << w[s]) - 1)
+    e = [u32(d[2 * i] + (d[2 * i + 1] << 8)) for i in range(4)]
+    x = u64((e[0] | (e[2] << 32)) + e[1] * 65536)                       # mad.wide.u32 e1, 65536, {e0, e2}
+    sh3 = 8 + w5
+    m3 = ((e[3] << sh3) & 0xffffffff) & (LOW29 & ~((1 << sh3) - 1))
+    assert m3 == (e[3] & ((1 << (21 - w5)) - 1)) << sh3
+    s3 = u32((e[3] >> (21 - w5)) + 1)
+    t = u64(x + (s3 | (m3 << 32)))
+    assert 1 <= t < (1 << 62)
+    qm1 = (t >> 61) - 1
+    r = (t + qm1) & M64
+    return r & ((LOW29 << 32) | 0xffffffff)
+
+
+def tc2_share(crow, xs):
+    kt = len(crow)
+    w, pos = limb_plan2(kt)
+    assert pos[7] + w[7] == 61
+    d = [0] * 8
+    for c, x in zip(crow, xs):
+        assert 0 <= x <= M64
+        for byte in range(8):
+            cst = c * pow(2, 8 * byte, P) % P
+            xb = (x >> (8 * byte)) & 0xff
+            for s in range(8):
+                d[s] += xb * ((cst >> pos[s]) & ((1 << w[s]) - 1))
+    return compose2(d, w, kt)
+
+
+def test_packed_tc2_limb_plan_and_compose_are_exact():
+    rng = random.Random(7)
+    for kt in range(2, 17):
+        for trial in range(200):
+            crow = [rng.choice(EXTREME_C + [rng.randrange(P)]) for _ in range(kt)]
+            xs = [rng.choice([0, M64, P, P - 1, (1 << 61) + 13, 1 << 63, rng.randrange(1 << 64)]) for _ in range(kt)]
+            assert tc2_share(crow, xs) == sum(c * x for c, x in zip(crow, xs)) % P
+        w, _ = limb_plan2(kt)
+        compose2([8 * kt * 255 * ((1 << w[s]) - 1) for s in range(8)], w, kt)      # every limb sum at its maximum
+        assert tc2_share([P - 1] * kt, [M64] * kt) == (P - 1) * M64 * kt % P
+
+
+def test_packed_tc2_draw_operand_is_congruent_to_gen_range():
+    """reduce_draw2: X = v + (v >> 61) as a u64 is congruent mod p to gen_range's v mod (p - 1) outside the flagged band"""
+    rng = random.Random(8)
+    for _ in range(20000):
+        v = rng.choice([rng.randrange(1 << 64), (rng.randrange(8) << 61) | ((1 << 61) - 33 - rng.randrange(1 << 20)),
+                        (7 << 61) | rng.randrange(1 << 61)])
+        hi, w1 = (v >> 32) & LOW29, v & 0xffffffff
+        if hi == LOW29 and w1 >= 0xffffffe0:
+            continue                                                       # the kernel raises `flag`; the host redoes the call
+        x = v + (v >> 61)
+        assert x <= M64 and v < (1 << 64) - 16
+        assert x % P == (v % (P - 1)) % P
+
+
+def walk_units2(grid, participants, unit_begin, units_per_p):
+    """packed_share_tc2_kernel's 32-bit unit bookkeeping: one conditional subtraction per step"""
+    unit_end, units_total = unit_begin + units_per_p, units_per_p * participants
+    step_p, step_u = grid // units_per_p, grid % units_per_p
+    seen = []
+    for cta in range(min(grid, units_total)):
+        p, u, unit = cta // units_per_p, unit_begin + cta % units_per_p, cta
+        while unit < units_total:
+            seen.append((p, u))
+            p, u = p + step_p, u + step_u
+            if u >= unit_end:
+                u -= units_per_p
+                p += 1
+            unit += grid
+    return seen
+
+
+def test_packed_tc2_unit_walk_covers_every_slice_exactly_once():
+    rng = random.Random(9)
+    for _ in range(300):
+        grid = rng.choice([1, 2, 3, 7, 148, 592])
+        participants, units_per_p, unit_begin = rng.randint(1, 9), rng.randint(1, 40), rng.choice([0, 1, 5, 813])
+        want = [(p, u) for p in range(participants) for u in range(unit_begin, unit_begin + units_per_p)]
+        assert sorted(walk_units2(grid, participants, unit_begin, units_per_p)) == want
+
+
+def test_packed_tc2_pair_layout_maps_every_draw_and_secret_once():
+    """stage_draws2 / the staging loop: (tile, row, chunk) of every draw chunk and secret word of a pass"""
+    for k, t in ((3, 2), (5, 4), (3, 4), (4, 2), (2, 8)):
+        dc, sc = t // 2, (k + 1) // 2
+        g = 4 // __import__("math").gcd(t, 4)
+        pairs, nb = g, t // __import__("math").gcd(t, 4)
+        assert pairs * 256 * t == 8 * 128 * nb                            # the pass's draws are whole keystream blocks
+        seen = {}
+        for slot in range(128 * nb):
+            gc0 = slot * 4
+            beta0, c0 = gc0 // dc, gc0 % dc
+            for cb in range(4):
+                gc = gc0 + cb
+                beta, c = gc // dc, gc % dc                               # what the chunk is: batch beta, chunk c
+                tile, row = (beta >> 8) * 2 + (beta & 1), (beta & 255) >> 1
+                # what the kernel computes from chunk 0 of the block plus a compile-time delta
+                tile0, row0 = (beta0 >> 8) * 2 + (beta0 & 1), (beta0 & 255) >> 1
+                if dc == 1:
+                    got = (tile0 + (cb & 1), row0 + (cb >> 1), c0)
+                elif dc == 2:
+                    got = (tile0 + (cb >> 1), row0, c0 + (cb & 1))
+                else:
+                    got = (tile0, row0, c0 + cb)
+                assert got == (tile, row, c)
+                assert (row0 & 7) + (cb >> 1 if dc == 1 else 0) < 8       # the delta stays inside the 8-row group
+                seen[(tile, row, c)] = seen.get((tile, row, c), 0) + 1
+        assert len(seen) == pairs * 2 * 128 * dc and set(seen.values()) == {1}
+        # secrets: thread r of pair q reads words 0..k-1 at element (q*256 + 2r)*k; E row r gets words 0..sc-1, O row r words k-sc..k-1
+        for r in range(128):
+            base = 2 * r * k
+            e_elems = [base + 2 * c + v for c in range(sc) for v in range(2)]
+            o_elems = [base + 2 * (k - sc + c) + v for c in range(sc) for v in range(2)]
+            for slot_i, el in enumerate(e_elems):
+                idx = slot_i                                             # image E: secret index = 2c + v
+                assert (el == base + idx) and (idx < k or el >= base + k)
+            for slot_i, el in enumerate(o_elems):
+                idx = slot_i - (k & 1)                                    # image O: half a chunk late for odd k
+                assert el == base + k + idx
