@@ -83,7 +83,7 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, mat, tc_image, tc_image_r, tc2_image;
+    DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image;
     int packed_path = SDA_PACKED_PATH_AUTO;
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
     std::vector<uint64_t> tc2_image_key;  // likewise for the paired-tile kernel's two images (packed_tc2.cu)
@@ -498,8 +498,9 @@ int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const Field
         CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
         ctx->tc2_image_key = key;
     }
+    CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
     CU(launch_packed_share_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
-                               (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
+                               (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
     return SDA_OK;
 }
 
@@ -892,7 +893,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image}) b->release();
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);

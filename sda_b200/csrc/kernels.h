@@ -101,9 +101,12 @@ bool packed_share_tc2_supported(int k, int t, int n, size_t dim);
 size_t packed_share_tc2_image_bytes(int k, int t, int n);
 void packed_share_tc2_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img);
 size_t packed_share_tc2_slice_batches(int k, int t, int n);
+// d_key_scratch: packed_share_tc2_key_scratch_bytes(P) bytes of device memory, 16-byte aligned (per-participant
+// constants of the keystream's first round, written by a small kernel ahead of the main one)
+size_t packed_share_tc2_key_scratch_bytes(size_t P);
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
-                                    const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
+                                    uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
 // fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,

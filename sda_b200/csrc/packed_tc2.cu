@@ -91,28 +91,56 @@ struct Shape2 {
     a += b; d ^= a; d = __funnelshift_l(d, d, 8);               \
     c += d; b ^= c; b = __funnelshift_l(b, b, 7);
 
+// Columns 1..3 of the first round do not depend on the block counter while it stays below 2^32 (state words 13..15
+// are zero then): they are per-participant constants, computed once per launch by chacha_prepare_kernel and loaded
+// instead of being recomputed for every block -- 3 of a block's 8 ROUNDS / 2 quarter rounds.
+struct ChaChaPre {
+    uint32_t w[12];     // x1,x5,x9,x13, x2,x6,x10,x14, x3,x7,x11,x15 after the first column round, counter high word 0
+};
+
+__global__ void chacha_prepare_kernel(const ChaChaKey *__restrict__ keys, size_t P, ChaChaPre *__restrict__ pre) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const uint32_t c[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
+    const ChaChaKey k = keys[p];
+    for (int col = 1; col < 4; col++) {
+        uint32_t a = c[col], b = k.w[col], cc = k.w[4 + col], d = 0;
+        SDA_QR2(a, b, cc, d)
+        pre[p].w[4 * (col - 1) + 0] = a;
+        pre[p].w[4 * (col - 1) + 1] = b;
+        pre[p].w[4 * (col - 1) + 2] = cc;
+        pre[p].w[4 * (col - 1) + 3] = d;
+    }
+}
+
+// one keystream block (counter b0 < 2^32) from the key and its precomputed first-round columns
 template <int ROUNDS>
-__device__ __forceinline__ void chacha_block2(const uint32_t (&k)[8], uint32_t b0, uint32_t b1, uint32_t (&o)[16]) {
+__device__ __forceinline__ void chacha_block2(const uint32_t (&k)[8], const uint32_t (&pre)[12], uint32_t b0, uint32_t (&o)[16]) {
     const uint32_t c0 = 0x61707865u, c1 = 0x3320646eu, c2 = 0x79622d32u, c3 = 0x6b206574u;
-    uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = c3;
-    uint32_t x4 = k[0], x5 = k[1], x6 = k[2], x7 = k[3];
-    uint32_t x8 = k[4], x9 = k[5], x10 = k[6], x11 = k[7];
-    uint32_t x12 = b0, x13 = b1, x14 = 0, x15 = 0;
-#pragma unroll 2
-    for (int i = 0; i < ROUNDS / 2; i++) {
-        SDA_QR2(x0, x4, x8, x12)
-        SDA_QR2(x1, x5, x9, x13)
-        SDA_QR2(x2, x6, x10, x14)
-        SDA_QR2(x3, x7, x11, x15)
+    uint32_t x0 = c0, x4 = k[0], x8 = k[4], x12 = b0;
+    uint32_t x1 = pre[0], x5 = pre[1], x9 = pre[2], x13 = pre[3];
+    uint32_t x2 = pre[4], x6 = pre[5], x10 = pre[6], x14 = pre[7];
+    uint32_t x3 = pre[8], x7 = pre[9], x11 = pre[10], x15 = pre[11];
+    SDA_QR2(x0, x4, x8, x12)                   // the one column of round 1 that sees the counter
+#pragma unroll 3
+    for (int i = 0; i < ROUNDS / 2 - 1; i++) {  // diagonal round, then the next column round
         SDA_QR2(x0, x5, x10, x15)
         SDA_QR2(x1, x6, x11, x12)
         SDA_QR2(x2, x7, x8, x13)
         SDA_QR2(x3, x4, x9, x14)
+        SDA_QR2(x0, x4, x8, x12)
+        SDA_QR2(x1, x5, x9, x13)
+        SDA_QR2(x2, x6, x10, x14)
+        SDA_QR2(x3, x7, x11, x15)
     }
+    SDA_QR2(x0, x5, x10, x15)
+    SDA_QR2(x1, x6, x11, x12)
+    SDA_QR2(x2, x7, x8, x13)
+    SDA_QR2(x3, x4, x9, x14)
     o[0] = x0 + c0;     o[1] = x1 + c1;     o[2] = x2 + c2;      o[3] = x3 + c3;
     o[4] = x4 + k[0];   o[5] = x5 + k[1];   o[6] = x6 + k[2];    o[7] = x7 + k[3];
     o[8] = x8 + k[4];   o[9] = x9 + k[5];   o[10] = x10 + k[6];  o[11] = x11 + k[7];
-    o[12] = x12 + b0;   o[13] = x13 + b1;   o[14] = x14;         o[15] = x15;
+    o[12] = x12 + b0;   o[13] = x13;        o[14] = x14;         o[15] = x15;
 }
 
 // draw v = (hi word w0, lo word w1) -> a u64 congruent to v mod (p - 1) modulo p:  v mod (p - 1) = (v & p) + 2 (v >> 61)
@@ -174,20 +202,26 @@ __device__ __forceinline__ bool elect_one() {
 // Chunk gc of the pass (16 bytes = two draws, stream order) belongs to batch gc / DC of the pass; batch beta sits in
 // tile pair beta / 256, tile E or O by its parity, row (beta % 256) / 2.
 template <class S, int ROUNDS>
-__device__ __forceinline__ void stage_draws2(const ChaChaKey *__restrict__ keys, uint32_t p, uint32_t u, int tid, uint8_t *sD,
-                                             unsigned *flag) {
-    uint32_t k[8];
-    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
-    const uint4 ka = __ldg(src), kb = __ldg(src + 1);
-    k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
-    k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
-    const uint64_t blk0 = (uint64_t)u * (uint32_t)(CTA2 * S::NB);
+__device__ __forceinline__ void stage_draws2(const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, uint32_t p,
+                                             uint32_t u, int tid, uint8_t *sD, unsigned *flag) {
+    uint32_t k[8], pre[12];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
+        const uint4 ka = __ldg(src), kb = __ldg(src + 1);
+        k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
+        k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
+        const uint4 *ps = reinterpret_cast<const uint4 *>(pres + p);
+        const uint4 pa = __ldg(ps), pb = __ldg(ps + 1), pc = __ldg(ps + 2);
+        pre[0] = pa.x; pre[1] = pa.y; pre[2] = pa.z; pre[3] = pa.w;
+        pre[4] = pb.x; pre[5] = pb.y; pre[6] = pb.z; pre[7] = pb.w;
+        pre[8] = pc.x; pre[9] = pc.y; pre[10] = pc.z; pre[11] = pc.w;
+    }
+    const uint32_t blk0 = u * (uint32_t)(CTA2 * S::NB);           // the launcher keeps a participant below 2^32 blocks
 #pragma unroll 1
     for (int nb = 0; nb < S::NB; nb++) {
         const uint32_t slot = nb * CTA2 + tid;                    // block of this pass, in stream order
-        const uint64_t blk = blk0 + slot;
         uint32_t w[16];
-        chacha_block2<ROUNDS>(k, (uint32_t)blk, (uint32_t)(blk >> 32), w);
+        chacha_block2<ROUNDS>(k, pre, blk0 + slot, w);
         uint32_t suspect = 0;
         // the block's four chunks: chunk 0 goes to `dst`, the others to compile-time offsets from it
         const uint32_t gc0 = slot * 4;
@@ -282,8 +316,8 @@ template <int K, int T, int N, int ROUNDS>
 __global__ void __launch_bounds__(CTA2, 1)
 packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
                         uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
-                        const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image, int64_t *__restrict__ out,
-                        unsigned *flag, int bulk_ok, int vec_ok) {
+                        const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,
+                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok) {
     typedef Shape2<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (PAIRS x {E, O} tiles x 128 rows x draws)
@@ -333,7 +367,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         } else {
             fill_secrets2<S, K>(secrets, ld, dim, p, u, tid, sIn);
         }
-        stage_draws2<S, ROUNDS>(keys, p, u, tid, sD, flag);
+        stage_draws2<S, ROUNDS>(keys, pres, p, u, tid, sD, flag);
     }
 
     for (uint32_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
@@ -393,7 +427,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
 
         // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
         if (more) {
-            stage_draws2<S, ROUNDS>(keys, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
+            stage_draws2<S, ROUNDS>(keys, pres, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
             if (!by_bulk(un)) fill_secrets2<S, K>(secrets, ld, dim, pn, un, tid, sIn);
         }
 
@@ -534,7 +568,8 @@ void build_b_image2(const Matrix &m, uint64_t p, uint8_t *img) {
 
 template <int K, int T, int N, int ROUNDS>
 cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
-                    size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out, unsigned *flag) {
+                    size_t n_batches, const ChaChaKey *keys, uint32_t *d_pre, const uint8_t *d_b_image, int64_t *out,
+                    unsigned *flag) {
     typedef Shape2<K, T, N> S;
     const size_t B = (dim + K - 1) / K;
     if (first_batch % S::PASS != 0 || first_batch > B) return cudaErrorInvalidValue;
@@ -560,9 +595,14 @@ cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size
     // 16-byte stores need every share row to start at an even element
     const int vec_ok = reinterpret_cast<uintptr_t>(out) % 16 == 0 && B % 2 == 0;
     const size_t full_in = dim / ((size_t)S::PASS * K), full_out = B / S::PASS;
+    // a participant's keystream stays below 2^32 blocks (B T / 8 of them): the counter's high word is 0
+    if ((B * (size_t)T + 7) / 8 >> 32) return cudaErrorInvalidValue;
+    ChaChaPre *pres = reinterpret_cast<ChaChaPre *>(d_pre);
+    chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
+    ++*lc.nlaunch;
     kern<<<(unsigned)grid, CTA2, smem, lc.stream>>>(secrets, ld, dim, B, (uint32_t)unit_begin, (uint32_t)units_per_p,
                                                     (uint32_t)units_total, (uint32_t)std::min<size_t>(full_in, 0xffffffffu),
-                                                    (uint32_t)std::min<size_t>(full_out, 0xffffffffu), keys,
+                                                    (uint32_t)std::min<size_t>(full_out, 0xffffffffu), keys, pres,
                                                     reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok);
     ++*lc.nlaunch;
     return cudaGetLastError();
@@ -603,15 +643,17 @@ size_t packed_share_tc2_slice_batches(int k, int t, int n) {
     return 0;
 }
 
+size_t packed_share_tc2_key_scratch_bytes(size_t P) { return P * sizeof(ChaChaPre); }
+
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
-                                    const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag) {
+                                    uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag) {
 #define X(K, T, N)                                                                                              \
     if (k == K && t == T && n == N) {                                                                           \
         *lc.kernel_name = "packed_share<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8, paired tiles";   \
-        if (rounds == 8) return launch2<K, T, N, 8>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_b_image, shares_out, flag); \
-        if (rounds == 12) return launch2<K, T, N, 12>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_b_image, shares_out, flag); \
-        return launch2<K, T, N, 20>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_b_image, shares_out, flag); \
+        if (rounds == 8) return launch2<K, T, N, 8>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_key_scratch, d_b_image, shares_out, flag); \
+        if (rounds == 12) return launch2<K, T, N, 12>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_key_scratch, d_b_image, shares_out, flag); \
+        return launch2<K, T, N, 20>(lc, secrets, ld, P, dim, first_batch, n_batches, keys, d_key_scratch, d_b_image, shares_out, flag); \
     }
     SDA_TC2_SHAPES(X)
 #undef X
