@@ -6,8 +6,11 @@ packed Shamir k=3 / n=5 (t=2) over p = 2^61-1, dim = 10M secrets per participant
 is one pass of the hot path over one resident tile of T participants per GPU:
     K2  sda_share_generate_dev   secrets[T][dim]      -> shares[T][5][B]      (B = ceil(dim/3))
     K3  sda_share_combine_dev x5 shares[T][c][B]      -> clerk_sum[c][B]      (one per clerk)
-    N>1 one NCCL reduce (uint64 sum) of clerk_sum[5][B] over the ranks + one mod-p pass on rank 0
+    N>1 sda_partial_sums_reduce_dev: one ncclReduce (uint64 sum) of clerk_sum[5][B] over the ranks + one mod-p pass
+        on rank 0, inside the library (torch.distributed only launches the ranks, hands rank 0's NCCL id to the
+        others and takes the max of the timings)
 (participants are sharded across GPUs: weak scaling, no other data-path collective).
+`kernels.config4_clerk_sum` / `kernels.config5_e2e` are BASELINE configs #4 and #5 at their named sizes per GPU.
 `value` = secrets processed by all ranks / max-over-ranks device time, inputs resident in HBM.
 `e2e`   = the same metric through the host-buffer C-ABI calls a Rust shim would make
           (sda_share_generate per participant, sda_share_combine per clerk), pinned host buffers,
@@ -56,8 +59,10 @@ def workload_config(args, world):
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle's literal restatement on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_step(O, scheme_o, modulus, dim, participants, threads, tag):
-    """generate + per-clerk combine for `participants` vectors of `dim`, one participant per thread"""
+def cpu_step(O, scheme_o, modulus, dim, participants, threads, tag, os_rng=False):
+    """generate + per-clerk combine for `participants` vectors of `dim`, one participant per thread.
+    os_rng: draw the sharing randomness the way the reference does (rand 0.3 `OsRng`: one getrandom(2) per word,
+    additive.rs:17,43 / packed_shamir.rs:40-43) instead of from the injected ChaCha20 stream of the parity mode."""
     import numpy as np
     n = scheme_o.share_count
     B = (dim + scheme_o.secret_count - 1) // scheme_o.secret_count
@@ -66,7 +71,7 @@ def cpu_step(O, scheme_o, modulus, dim, participants, threads, tag):
     t0 = time.perf_counter()
 
     def work(i):
-        rng = O.rng_from_seed_bytes(hashlib.sha256(b"%s/%d" % (tag.encode(), i)).digest())
+        rng = O.rng_os() if os_rng else O.rng_from_seed_bytes(hashlib.sha256(b"%s/%d" % (tag.encode(), i)).digest())
         shares[i] = O.share_generate(scheme_o, secrets[i], rng)
 
     ths = []
@@ -115,12 +120,19 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps * cores * dim_s / dt
     sample = f"{cores} participants x {dim_s} secrets per step (of dim 10M), one participant per thread"
+    # the same loop with the reference's own randomness source (one getrandom(2) per draw), one bounded step
+    dim_os = max(10_000, dim_s // 4)
+    t_os = cpu_step(O, so, m, dim_os, cores, cores, "os", os_rng=True)
+    faithful = {"value": cores * dim_os / t_os, "unit": UNIT, "cores": cores, "kind": "port",
+                "rng": "OsRng: one getrandom(2) per 32-bit word, as rand 0.3 does (additive.rs:17,43, packed_shamir.rs:40-43)",
+                "sample": f"{cores} participants x {dim_os} secrets, one step"}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "i64 (mod 2^61-1, 128-bit products)", "data": "synthetic",
-        "config": dict(workload_config(args, 1), sample=sample),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "rng": "injected ChaCha20 stream (the parity mode)", "faithful_os_rng": faithful},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference = snipsco/sda's CPU algorithm restated in C (oracle/sda_oracle.c: per-batch Newton "
                 "interpolation like tss 0.2, widened to 128-bit products for the 61-bit prime; injected ChaCha20 "
@@ -245,6 +257,144 @@ class ClockSampler:
         return out
 
 
+# ---------------------------------------------------------------------------------------------------
+# BASELINE configs #4 and #5 at their named sizes, through the same context (reported under `kernels`)
+# ---------------------------------------------------------------------------------------------------
+def run_config4(ctx, stream, torch, dist, world, rank, peak):
+    """config #4: one clerk's job of the k=5/n=9 scheme, [65536][2M] share rows (1.05 TB), participants sharded over the
+    ranks; every rank walks its 65536/N rows in resident tiles with sda_share_combine_dev (running sum), then ONE
+    sda_partial_sums_reduce_dev.  The synthetic tile (identical on every rank, filled untimed) is re-read for every tile
+    of the shard: 8 B of HBM traffic per share element either way."""
+    from sda_b200 import params
+    s4 = params.config4()
+    p, L, rows_total = s4.modulus, 2_000_000, 65536
+    rows_rank = rows_total // world
+    R = min(rows_rank, 4096)                      # 65.5 GB resident
+    tiles = rows_rank // R
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    with torch.cuda.stream(stream):
+        d_tile = torch.empty((R, L), dtype=torch.int64, device="cuda")
+        d_acc = torch.empty(L, dtype=torch.int64, device="cuda")
+        d_one = torch.empty(L, dtype=torch.int64, device="cuda")
+        ctx.synth_fill_dev(4, p, 0, R * L, d_tile)
+        ctx.share_combine_dev(s4, d_tile, L, R, L, d_one)            # warm-up and the check's column sums of one tile
+        if world > 1:
+            ctx.partial_sums_reduce_dev(p, d_acc.zero_(), L, 0)      # communicator warm-up
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b, c = ev(), ev(), ev()
+        a.record(stream)
+        for t in range(tiles):
+            ctx.share_combine_dev(s4, d_tile, L, R, L, d_acc, d_acc_in=d_acc if t else None)
+        b.record(stream)
+        if world > 1:
+            ctx.partial_sums_reduce_dev(p, d_acc, L, 0)
+        c.record(stream)
+        ctx.synchronize()
+        ms = torch.tensor([a.elapsed_time(c), b.elapsed_time(c)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ok = None
+        if rank == 0:   # sampled columns: total == (tiles * world) * (column sum of one tile) mod p, in Python integers
+            cols = [0, 1, 77, L // 2, L - 1]
+            one = [int(d_one[cidx]) for cidx in cols]
+            got = [int(d_acc[cidx]) for cidx in cols]
+            ok = got == [(v * tiles * world) % p for v in one]
+        del d_tile, d_acc, d_one
+    torch.cuda.empty_cache()
+    total_ms, reduce_ms = float(ms[0]), float(ms[1])
+    return {"ms": total_ms, "share_elements_per_s": rows_total * L / (total_ms * 1e-3), "rows_per_gpu": rows_rank,
+            "rows_total": rows_total, "L": L, "resident_tile_rows": R, "GBps_per_gpu": rows_rank * L * 8 / (total_ms * 1e-3) / 1e9,
+            "frac_of_hbm_per_gpu": rows_rank * L * 8 / (total_ms * 1e-3) / 1e9 / peak,
+            "collective_ms": reduce_ms if world > 1 else 0.0, "collective_share_of_step": reduce_ms / total_ms if world > 1 else 0.0,
+            "correct": ok, "note": "config #4 clerk sum at size: combine over the rank's rows (running sum over resident tiles) + "
+                                   "one NCCL reduce of [2M] u64 + mod pass inside the library; strong scaling over N"}
+
+
+def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
+    """config #5, the federated proxy end to end: float updates [P][25M] -> fixed point (2^-24) -> ChaCha mask -> packed Shamir
+    k=3/n=7 (t=4) shares summed per clerk in TMEM (fused kernel) -> one library-side NCCL reduce of the clerk sums and of the
+    mask sums -> reveal from the 7 clerks -> unmask -> mean.  1024 participants per GPU (8192 at 8 GPUs = the named size)."""
+    from sda_b200 import LinearMaskingScheme as LMS
+    from sda_b200 import params
+    FRAC = 24
+    p = params.P61
+    scheme = params.config5()
+    n, dim, P, Pt = scheme.output_size(), 25_000_000, participants, tile
+    B = scheme.batches(dim)
+    ms_ = LMS.ChaCha(p, dim, 128)
+    words = 4
+    stages = {k: 0.0 for k in ("encode_mask", "share_gen_clerk_sum", "mask_expand", "reduce", "reveal", "unmask_decode")}
+    sd = lambda tag: hashlib.sha256(tag.encode()).digest()   # noqa: E731
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        ctx.synchronize()
+        stages[name] += a.elapsed_time(b)
+
+    with torch.cuda.stream(stream):
+        d_x = torch.empty((Pt, dim), dtype=torch.float32, device="cuda")
+        d_q = torch.empty((Pt, dim), dtype=torch.int64, device="cuda")
+        d_m = torch.empty((Pt, dim), dtype=torch.int64, device="cuda")
+        d_sum = torch.zeros((n, B), dtype=torch.int64, device="cuda")
+        d_seedw = torch.zeros((P, words), dtype=torch.int64, device="cuda")
+        truth = torch.zeros(dim, dtype=torch.float64, device="cuda")
+        gen = torch.Generator(device="cuda")
+        for t0 in range(0, P, Pt):
+            pt = min(Pt, P - t0)
+            gen.manual_seed(1234 + rank * 100003 + t0)
+            d_x[:pt].normal_(generator=gen)
+            truth += d_x[:pt].sum(dim=0, dtype=torch.float64)
+            stream.synchronize()
+
+            def encode_mask():
+                ctx.fixed_encode_dev(p, FRAC, d_x, pt * dim, d_q)
+                for i in range(pt):
+                    ctx.mask_dev(ms_, d_q[i], dim, sd(f"fed/mask/{rank}/{t0 + i}"), d_seedw[t0 + i], d_m[i])
+            timed("encode_mask", encode_mask)
+            seeds = b"".join(sd(f"fed/share/{rank}/{t0 + i}") for i in range(pt))
+            timed("share_gen_clerk_sum",
+                  lambda: ctx.share_generate_combine_dev(scheme, d_m, dim, pt, dim, seeds, d_sum, d_acc_in=d_sum if t0 else None))
+        del d_x, d_q, d_m
+        d_mask = torch.empty(dim, dtype=torch.int64, device="cuda")
+        timed("mask_expand", lambda: ctx.mask_combine_dev(ms_, d_seedw, P, words, d_mask))
+
+        def reduce_all():
+            ctx.partial_sums_reduce_dev(p, d_sum, n * B, 0)
+            ctx.partial_sums_reduce_dev(p, d_mask, dim, 0)
+        timed("reduce", reduce_all)
+        if world > 1:
+            dist.reduce(truth, dst=0)
+        ok, err = None, None
+        if rank == 0:
+            d_rec = torch.empty(dim, dtype=torch.int64, device="cuda")
+            timed("reveal", lambda: ctx.secret_reconstruct_dev(scheme, dim, list(range(n)), d_sum, B, n, B, d_rec))
+            d_mean = torch.empty(dim, dtype=torch.float32, device="cuda")
+
+            def finish():
+                ctx.unmask_dev(ms_, d_mask, d_rec, dim, d_rec)
+                ctx.fixed_decode_dev(p, FRAC, world * P, d_rec, dim, d_mean)
+            timed("unmask_decode", finish)
+            err = float((d_mean.double() - truth / (world * P)).abs().max())
+            ok = err < 2.0 ** -(FRAC - 1)
+            del d_rec, d_mean
+        del d_sum, d_seedw, d_mask, truth
+    torch.cuda.empty_cache()
+    t = torch.tensor([sum(stages.values())] + [stages[k] for k in stages], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t[0])
+    return {"ms": total_ms, "elements_per_s": world * P * dim / (total_ms * 1e-3), "participants_total": world * P,
+            "participants_per_gpu": P, "dim": dim, "ms_per_stage_max_over_ranks": {k: float(v) for k, v in zip(stages, t[1:])},
+            "max_abs_error_of_mean": err, "correct": ok,
+            "note": "config #5 federated proxy, device-resident, CUDA events per stage (max over ranks); the named size is "
+                    "8192 participants on 8 GPUs, fewer GPUs run the same 1024 participants per GPU (weak scaling)"}
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -270,7 +420,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     import sda_b200
-    from sda_b200 import multi, params
+    from sda_b200 import params
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -291,6 +441,13 @@ def run_ours(args):
 
     ctx = sda_b200.Context(local, rng_rounds=args.rounds)
     ctx.set_packed_path({"auto": 0, "cuda": 1, "tc": 2, "tc1": 3}[args.packed_path])
+    if world > 1:
+        # the library's own NCCL communicator (C ABI): rank 0 creates the id, torch.distributed only carries the 128 bytes
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.tensor(list(sda_b200.Context.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        ctx.comm_init_rank(bytes(idt.cpu().tolist()), world, rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     scheme = params.config3()
@@ -320,9 +477,8 @@ def run_ours(args):
                 ctx.share_combine_dev(scheme, d_sh[:, cl, :], n * B, T, B, d_sum[cl])
             if world > 1:
                 # one collective: canonical partials < p summed as 64-bit integers (<= 8 of them cannot wrap),
-                # then one mod-p pass on the root (sda_b200/multi.py, tests/test_multi_gloo.py)
-                multi.reduce_partial_sums(d_sum, p, dst=0,
-                                          final_mod=lambda t: ctx.mod_reduce_dev(p, t, n * B, d_tot, unsigned=True))
+                # then one mod-p pass on the root -- sda_partial_sums_reduce_dev, NCCL called by the library
+                ctx.partial_sums_reduce_dev(p, d_sum, n * B, 0)
             c.record(stream)
             if timed:
                 return a, b, c
@@ -488,13 +644,21 @@ def run_ours(args):
     h2d = Te * dim * 8 + n * Te * B * 8
     d2h = Te * n * B * 8 + n * B * 8
 
+    # ---- configs #4 and #5 at size (every rank takes part; the big buffers of the main workload are released first) ----
+    peak, peak_src = load_peaks()
+    cfg4 = cfg5 = None
+    if not args.no_configs45:
+        del d_sec, d_sh, d_sum, d_tot
+        torch.cuda.empty_cache()
+        cfg4 = run_config4(ctx, stream, torch, dist, world, rank, peak)
+        cfg5 = run_config5(ctx, stream, torch, dist, world, rank, args.cfg5_participants, 64)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel (K2 share-gen) --------------------------------------------
-    peak, peak_src = load_peaks()
     alg_bytes = T * (dim * 8 + n * B * 8)                       # read secrets + write shares
     gen_avg_ms = sum(gen_ms) / len(gen_ms)
     achieved = alg_bytes / (gen_avg_ms * 1e-3) / 1e9
@@ -520,10 +684,11 @@ def run_ours(args):
                                           "note": "sda_share_generate_combine_dev: reads 8 B per secret, shares never "
                                                   "materialised; not part of `value`"}} if fused_ms else {}),
         **({k: dict(v, frac_of_hbm=v["GBps"] / peak) for k, v in cfg2.items()} if cfg2 else {}),
+        **({"config4_clerk_sum": cfg4} if cfg4 else {}), **({"config5_e2e": cfg5} if cfg5 else {}),
         "clerk_combine_x5": {"ms": comb_avg_ms, "share_elements_per_s": n * T * B / (comb_avg_ms * 1e-3),
                              "GBps": comb_bytes / (comb_avg_ms * 1e-3) / 1e9,
                              "frac_of_hbm": comb_bytes / (comb_avg_ms * 1e-3) / 1e9 / peak,
-                             "includes": "NCCL reduce + mod pass" if world > 1 else "5 combine launches"},
+                             "includes": "5 combine launches + library-side NCCL reduce + mod pass" if world > 1 else "5 combine launches"},
     }
 
     # ---- cpu baseline beside it (bounded sample, rank 0, N=1 only) ---------------------------------
@@ -572,6 +737,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-round-sweep", action="store_true", help="skip the ChaCha12/ChaCha8 share-gen launches")
+    ap.add_argument("--no-configs45", action="store_true", help="skip the config #4 / config #5 legs (profiling runs)")
+    ap.add_argument("--cfg5-participants", type=int, default=1024, help="config #5 participants per GPU (8192 / 8)")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="target CPU seconds per reference step")
     ap.add_argument("--ref-dim", type=int, default=500_000)
     args = ap.parse_args()

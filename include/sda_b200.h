@@ -93,7 +93,11 @@ void        sda_ctx_destroy(sda_ctx *ctx);
  * sda_ctx_create on this thread) */
 const char *sda_last_error(const sda_ctx *ctx);
 /* ChaCha rounds of the injected sharing / Full-mask randomness: 8, 12 or 20 (default 20).
- * The ChaCha *mask scheme* (chacha.rs) is wire format and always uses 20. */
+ * The ChaCha *mask scheme* (chacha.rs) is wire format and always uses 20.
+ * SECURITY: this randomness is what hides the secrets.  Fewer than 20 rounds trades margin for speed (12 is what
+ * rand >= 0.8 `StdRng` uses, 8 has no margin to speak of); leave the default unless the deployment has decided
+ * otherwise.  Every call needs its OWN 32-byte rng_seed from a CSPRNG: the same seed given to sda_mask and to
+ * sda_share_generate yields the same keystream for both (no domain separation), i.e. correlated mask and shares. */
 int         sda_ctx_set_rng_rounds(sda_ctx *ctx, int rounds);
 int         sda_ctx_get_rng_rounds(const sda_ctx *ctx);
 /* Which kernels evaluate the packed-Shamir maps over 2^61-1 (share generation for the instantiated
@@ -191,7 +195,8 @@ int sda_share_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64
 
 /* Fused participant->clerk path for one box: shares of P participants are
  * generated and summed per clerk without materialising [P][n][B]:
- * out[n][B] (+= d_acc_in[n][B] if given) = sum_p generate(secrets[p]) . */
+ * out[n][B] (+= d_acc_in[n][B] if given) = sum_p generate(secrets[p]) .
+ * d_acc_in is NULL, equal to d_out (in place), or disjoint from it. */
 int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets,
                                    size_t secrets_ld, size_t P, size_t dim, const uint8_t *seeds,
                                    const int64_t *d_acc_in, int64_t *d_out);

@@ -111,6 +111,17 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _out(out, shape):
+    """a caller-provided output array the C side may write `shape` int64 elements into, or a fresh one"""
+    count = int(np.prod(shape))
+    if out is None:
+        return np.empty(shape, dtype=np.int64)
+    if not isinstance(out, np.ndarray) or out.dtype != np.int64 or not out.flags.c_contiguous or not out.flags.writeable \
+            or out.size < count:
+        raise ValueError(f"out must be a writeable C-contiguous int64 array of at least {count} elements")
+    return out
+
+
 def _seed(rng_seed):
     """32 bytes of entropy; the reference draws from OsRng at this point (additive.rs:17, full.rs:16)."""
     s = os.urandom(32) if rng_seed is None else bytes(rng_seed)
@@ -214,8 +225,7 @@ class Context:
     def share_generate(self, scheme, secrets, rng_seed=None, out=None):
         sec = _i64(secrets)
         n, B = scheme.output_size(), scheme.batches(len(sec))
-        if out is None:
-            out = np.empty((n, B), dtype=np.int64)
+        out = _out(out, (n, B))
         self.check(self._lib.sda_share_generate(self._h, C.byref(scheme.c), _ptr(sec), len(sec), _seed(rng_seed),
                                                 _ptr(out)))
         return out
@@ -225,8 +235,7 @@ class Context:
         if isinstance(shares, np.ndarray) and shares.ndim == 2 and shares.dtype == np.int64:
             sh = np.ascontiguousarray(shares)
             P, L = sh.shape
-            if out is None:
-                out = np.empty(L if P else 0, dtype=np.int64)
+            out = _out(out, (L if P else 0,))
             self.check(self._lib.sda_share_combine(self._h, C.byref(scheme.c), _ptr(sh), P, L, _ptr(out)))
             return out
         rows = [_i64(r) for r in shares]
@@ -234,8 +243,7 @@ class Context:
         ptrs = (C.c_void_p * max(P, 1))(*[r.ctypes.data for r in rows])
         lens = (C.c_size_t * max(P, 1))(*[len(r) for r in rows])
         L = len(rows[0]) if P else 0
-        if out is None:
-            out = np.empty(L, dtype=np.int64)
+        out = _out(out, (L,))
         n = C.c_size_t(0)
         self.check(self._lib.sda_share_combine_rows(self._h, C.byref(scheme.c), ptrs, lens, P, _ptr(out), C.byref(n)))
         return out[:n.value]
@@ -299,9 +307,41 @@ class Context:
 
     def share_generate_combine_dev(self, scheme, d_secrets, secrets_ld, P, dim, seeds, d_out, d_acc_in=None):
         seeds = bytes(seeds)
+        if len(seeds) != 32 * P:
+            raise ValueError("seeds must be P x 32 bytes")
         buf = (C.c_uint8 * max(len(seeds), 1)).from_buffer_copy(seeds or b"\0")
         self.check(self._lib.sda_share_generate_combine_dev(self._h, C.byref(scheme.c), _dev_ptr(d_secrets), secrets_ld,
                                                             P, dim, buf, _dev_ptr(d_acc_in), _dev_ptr(d_out)))
+
+    # -- multi-GPU clerk sum: the one exchange of the path, NCCL inside the library ------------
+    @staticmethod
+    def nccl_unique_id():
+        """128 bytes rank 0 hands to the other ranks (any transport) before comm_init_rank"""
+        lib = _lib.load()
+        buf = (C.c_uint8 * 128)()
+        rc = lib.sda_nccl_unique_id(buf)
+        if rc:
+            raise SdaClientError(rc, lib.sda_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init_rank(self, unique_id, nranks, rank):
+        """collective: every rank calls it with the same id"""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self.check(self._lib.sda_ctx_comm_init_rank(self._h, buf, nranks, rank))
+
+    def comm_rank(self):
+        return self._lib.sda_ctx_comm_rank(self._h)
+
+    def comm_size(self):
+        return self._lib.sda_ctx_comm_size(self._h)
+
+    def partial_sums_reduce_dev(self, modulus, d_partials, count, root=0):
+        """in place: this rank's canonical column sums -> (on `root`) the sums over all ranks mod `modulus`"""
+        self.check(self._lib.sda_partial_sums_reduce_dev(self._h, modulus, _dev_ptr(d_partials), count, root))
+
+    def share_combine_ranks_dev(self, scheme, d_shares, ld, P_local, L, d_out, d_acc_in=None, root=0):
+        self.check(self._lib.sda_share_combine_ranks_dev(self._h, C.byref(scheme.c), _dev_ptr(d_shares), ld, P_local, L,
+                                                         _dev_ptr(d_acc_in), _dev_ptr(d_out), root))
 
     def mod_reduce_dev(self, modulus, d_in, n, d_out, unsigned=False):
         f = self._lib.sda_mod_reduce_u64_dev if unsigned else self._lib.sda_mod_reduce_dev

@@ -85,6 +85,7 @@ struct sda_ctx {
     std::string err;
     DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image;
     int packed_path = SDA_PACKED_PATH_AUTO;
+    bool debug_force_reject = false;   // SDA_B200_DEBUG_FORCE_REJECT=1 at context creation: treat the fused kernel's flag as set
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
     std::vector<uint64_t> tc2_image_key;  // likewise for the paired-tile kernel's two images (packed_tc2.cu)
     std::vector<uint64_t> tc_image_r_key; // (k, m', R) likewise for the reconstruction operand
@@ -281,7 +282,9 @@ int share_matrix_cached(sda_ctx *ctx, const Packed &pk, Matrix *M) {
     key.insert(key.end(), pk.a.begin(), pk.a.end());
     key.insert(key.end(), pk.b.begin(), pk.b.end());
     if (key != ctx->m_key) {
-        OK(share_matrix(ctx, pk, &ctx->m_cached));
+        Matrix fresh;                              // a failure part-way must not leave a half-written matrix under the old key
+        OK(share_matrix(ctx, pk, &fresh));
+        ctx->m_cached = fresh;
         ctx->m_key = key;
     }
     *M = ctx->m_cached;
@@ -350,6 +353,8 @@ int upload_keys(sda_ctx *ctx, const uint8_t *seeds, size_t P) {
     CU(ctx->keys.reserve(P * sizeof(ChaChaKey)));
     CU(cudaMemcpyAsync(ctx->keys.p, k.data(), P * sizeof(ChaChaKey), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // k goes out of scope
+    volatile uint32_t *wipe = reinterpret_cast<volatile uint32_t *>(k.data());   // the host copy of the keys does not linger
+    for (size_t i = 0; i < P * 8; i++) wipe[i] = 0;
     return SDA_OK;
 }
 
@@ -615,7 +620,9 @@ int reconstruct_core(sda_ctx *ctx, const sda_sharing_scheme *s, size_t dimension
                                (uint64_t)s->omega_shares};
     rkey.insert(rkey.end(), indices, indices + m);
     if (rkey != ctx->r_key) {
-        OK(reconstruct_matrix(ctx, pk, indices, m, &ctx->r_cached));
+        Matrix fresh;
+        OK(reconstruct_matrix(ctx, pk, indices, m, &fresh));
+        ctx->r_cached = fresh;
         ctx->r_key = rkey;
     }
     const Matrix &R = ctx->r_cached;
@@ -882,6 +889,8 @@ int sda_ctx_create(int device, sda_ctx **out) {
         return SDA_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    const char *force = getenv("SDA_B200_DEBUG_FORCE_REJECT");
+    c->debug_force_reject = force && force[0] == '1';
     *out = c;
     return SDA_OK;
 }
@@ -893,6 +902,10 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     DeviceGuard g(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_release(ctx);
+    // keys, their derived constants and materialised draw streams are secret material: zero them before the memory
+    // goes back to the allocator
+    for (DevBuf *b : {&ctx->keys, &ctx->keys_pre, &ctx->draws})
+        if (b->p) cudaMemset(b->p, 0, b->cap);
     for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
@@ -1050,12 +1063,25 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
             OK(ensure_tc_image(ctx, pk, M));
             OK(upload_keys(ctx, seeds, P));
             OK(clear_flags(ctx));
+            // In place (d_acc_in == d_out) the kernel must not overwrite the running sum before the rejection flag is
+            // known: a redo would start from a sum that already holds this call's (wrong) contribution.  The sums then
+            // go to scratch and are copied over the accumulator only after the flag read 0.
+            int64_t *d_dst = d_out;
+            if (d_acc_in == d_out) {
+                CU(ctx->aux.reserve(n * B * sizeof(int64_t)));
+                d_dst = (int64_t *)ctx->aux.p;
+            }
             CU(launch_packed_share_combine_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
                                               (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_acc_in,
-                                              d_out, ctx->d_flag));
+                                              d_dst, ctx->d_flag));
             unsigned rejected = 0;
             OK(read_flags(ctx, &rejected, nullptr));
-            if (!rejected) return SDA_OK;
+            if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)
+            if (!rejected) {
+                if (d_dst != d_out)
+                    CU(cudaMemcpyAsync(d_out, d_dst, n * B * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+                return SDA_OK;
+            }
             // a rejected gen_range word somewhere (p ~ 2^-57 per draw): redo on the materialising path below
         }
     }

@@ -623,7 +623,7 @@ template <int K, int T, int N, int ROUNDS>
 __global__ void __launch_bounds__(CTA)
 packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t P,
                                const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
-                               const int64_t *__restrict__ acc_in, int64_t *__restrict__ out, unsigned *flag, int bulk_ok) {
+                               const int64_t *acc_in, int64_t *out, unsigned *flag, int bulk_ok) {   // acc_in may equal out
     typedef FusedShape<K, T, N> F;
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];

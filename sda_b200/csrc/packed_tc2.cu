@@ -160,21 +160,36 @@ __device__ __forceinline__ uint64_t reduce_draw2(uint32_t w0, uint32_t w1, uint3
 // 0,8,16,24,32,40,40+W5,48+W5).  e0..e3 are 32-bit; X = e0 + e1 2^16 + e2 2^32 < 2^61 + 2^48 is one wide multiply
 // whose addend is the register pair (e0, e2); e3 2^{40+W5} == (e3 mod 2^{21-W5}) 2^{40+W5} + (e3 >> (21-W5)) because
 // 2^61 == 1; t = value + 1 lies in [1, 2^62) and the last four instructions are packed_tc.cu's.
+#ifndef SDA_TC2_XWIDE
+#define SDA_TC2_XWIDE 0      // 1: X by IMAD.WIDE with a run-time multiplier (one FMA-pipe instruction) instead of LEA + LEA.HI.X
+#endif
+#ifndef SDA_TC2_FINAL_X
+#define SDA_TC2_FINAL_X 1    // 1: the final 64-bit add takes its high addend from a register (IMAD.X) instead of a sign extension
+#endif
 template <int W5>
-__device__ __forceinline__ uint64_t compose2(const uint32_t (&d)[8]) {
+__device__ __forceinline__ uint64_t compose2(const uint32_t (&d)[8], uint32_t two16) {
     const uint32_t e0 = d[0] + (d[1] << 8), e1 = d[2] + (d[3] << 8);
     const uint32_t e2 = d[4] + (d[5] << 8), e3 = d[6] + (d[7] << 8);
     uint64_t x;
+#if SDA_TC2_XWIDE
+    // two16 == 65536 is a kernel parameter so that ptxas keeps the multiply (it turns a literal into two shifts-and-adds)
+    asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, %4, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1), "r"(two16));
+#else
     asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, 65536, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1));
+#endif
     constexpr uint32_t SH3 = 8 + W5;                                  // position of e3 inside the high word
     const uint32_t m3 = (e3 << SH3) & (LOW29 & ~((1u << SH3) - 1u));
     const uint32_t s3 = (e3 >> (21 - W5)) + 1u;                       // + 1: t == value + 1
     const uint64_t t = x + pack(s3, m3);
     uint32_t t_lo, t_hi;
     unpack(t, t_lo, t_hi);
-    const int64_t qm1 = (int64_t)(int32_t)((t_hi >> 29) - 1u);        // floor((t - 1) / p) - 1 in {-1, 0}
+    const uint32_t qm1 = (t_hi >> 29) - 1u;                           // floor((t - 1) / p) - 1 in {-1, 0} as two's complement
     uint32_t r_lo, r_hi;
-    unpack(t + (uint64_t)qm1, r_lo, r_hi);
+#if SDA_TC2_FINAL_X
+    unpack(t + pack(qm1, qm1), r_lo, r_hi);                           // the 64-bit value -1 or 0: both words equal qm1
+#else
+    unpack(t + (uint64_t)(int64_t)(int32_t)qm1, r_lo, r_hi);
+#endif
     return pack(r_lo, r_hi & LOW29);
 }
 
@@ -201,21 +216,31 @@ __device__ __forceinline__ bool elect_one() {
 // the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to.
 // Chunk gc of the pass (16 bytes = two draws, stream order) belongs to batch gc / DC of the pass; batch beta sits in
 // tile pair beta / 256, tile E or O by its parity, row (beta % 256) / 2.
+// a participant's key and first-round constants, loaded well ahead of the keystream that needs them (the loads are
+// the only global-memory latency on a pass's critical path)
+struct KeyRegs {
+    uint4 ka, kb, pa, pb, pc;
+};
+__device__ __forceinline__ KeyRegs load_keys2(const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, uint32_t p) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
+    const uint4 *ps = reinterpret_cast<const uint4 *>(pres + p);
+    KeyRegs r;
+    r.ka = __ldg(src);
+    r.kb = __ldg(src + 1);
+    r.pa = __ldg(ps);
+    r.pb = __ldg(ps + 1);
+    r.pc = __ldg(ps + 2);
+    return r;
+}
+
 template <class S, int ROUNDS>
-__device__ __forceinline__ void stage_draws2(const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, uint32_t p,
-                                             uint32_t u, int tid, uint8_t *sD, unsigned *flag) {
+__device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int tid, uint8_t *sD, unsigned *flag) {
     uint32_t k[8], pre[12];
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
-        const uint4 ka = __ldg(src), kb = __ldg(src + 1);
-        k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
-        k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
-        const uint4 *ps = reinterpret_cast<const uint4 *>(pres + p);
-        const uint4 pa = __ldg(ps), pb = __ldg(ps + 1), pc = __ldg(ps + 2);
-        pre[0] = pa.x; pre[1] = pa.y; pre[2] = pa.z; pre[3] = pa.w;
-        pre[4] = pb.x; pre[5] = pb.y; pre[6] = pb.z; pre[7] = pb.w;
-        pre[8] = pc.x; pre[9] = pc.y; pre[10] = pc.z; pre[11] = pc.w;
-    }
+    k[0] = kr.ka.x; k[1] = kr.ka.y; k[2] = kr.ka.z; k[3] = kr.ka.w;
+    k[4] = kr.kb.x; k[5] = kr.kb.y; k[6] = kr.kb.z; k[7] = kr.kb.w;
+    pre[0] = kr.pa.x; pre[1] = kr.pa.y; pre[2] = kr.pa.z; pre[3] = kr.pa.w;
+    pre[4] = kr.pb.x; pre[5] = kr.pb.y; pre[6] = kr.pb.z; pre[7] = kr.pb.w;
+    pre[8] = kr.pc.x; pre[9] = kr.pc.y; pre[10] = kr.pc.z; pre[11] = kr.pc.w;
     const uint32_t blk0 = u * (uint32_t)(CTA2 * S::NB);           // the launcher keeps a participant below 2^32 blocks
 #pragma unroll 1
     for (int nb = 0; nb < S::NB; nb++) {
@@ -294,17 +319,17 @@ __device__ __forceinline__ void st_global_1(char *ptr, uint64_t a) {
 // the odd batch's shares composed and both batches' shares stored: share row j of the pair at `off + j row_bytes`
 template <class S, int N>
 __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint64_t (&re)[N], char *ptr, size_t row_bytes,
-                                           bool fast_store, uint32_t live) {
+                                           bool fast_store, uint32_t live, uint32_t two16) {
     if (fast_store) {
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            st_global_v2(ptr, re[j], compose2<S::W5>(d[j]));
+            st_global_v2(ptr, re[j], compose2<S::W5>(d[j], two16));
             ptr += row_bytes;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < N; j++) {
-            const uint64_t ro = compose2<S::W5>(d[j]);
+            const uint64_t ro = compose2<S::W5>(d[j], two16);
             if (live >= 1) st_global_1(ptr, re[j]);
             if (live == 2) st_global_1(ptr + 8, ro);
             ptr += row_bytes;
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(CTA2, 1)
 packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
                         uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
                         const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,
-                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok) {
+                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok, uint32_t two16) {
     typedef Shape2<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (PAIRS x {E, O} tiles x 128 rows x draws)
@@ -361,44 +386,60 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
     // a pass that lies wholly inside its vector arrives by bulk copy when the source is 16-byte aligned (bulk_ok)
     auto by_bulk = [&](uint32_t uu) { return bulk_ok != 0 && uu < full_in_units; };
 
+    // output address of (p, u): share row 0, this thread's even batch of the pass's first pair.  A step adds step_p
+    // participants and step_u passes; when the pass index wraps, one participant more and units_per_p passes fewer.
+    char *opass = reinterpret_cast<char *>(out + (size_t)p * N * B + (size_t)u * S::PASS + 2 * tid);
+    const int64_t step_bytes = 8 * ((int64_t)step_p * N * (int64_t)B + (int64_t)step_u * S::PASS);
+    const int64_t wrap_bytes = 8 * ((int64_t)N * (int64_t)B - (int64_t)units_per_p * S::PASS);
     if (blockIdx.x < units_total) {
         if (by_bulk(u)) {
             if (tid == 0) bulk_load_secrets2<S, K>(secrets, ld, p, u, sin_addr, landed_bar);
         } else {
             fill_secrets2<S, K>(secrets, ld, dim, p, u, tid, sIn);
         }
-        stage_draws2<S, ROUNDS>(keys, pres, p, u, tid, sD, flag);
+        stage_draws2<S, ROUNDS>(load_keys2(keys, pres, p), u, tid, sD, flag);
     }
 
     for (uint32_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
+        // this CTA's next unit; its key is requested now and used after the staging barrier
+        uint32_t pn = p + step_p, un = u + step_u;
+        if (un >= unit_end) {
+            un -= units_per_p;
+            pn++;
+        }
+        const bool more = unit + gridDim.x < units_total;
+        KeyRegs knext;
+        if (more) knext = load_keys2(keys, pres, pn);
         // ---- this thread's 2K secrets of every pair (batches 2 tid, 2 tid + 1 of the pair): K aligned 16-byte words
         //      of the raw vector, which are the operand chunks as they are -------------------------------------------
         if (by_bulk(u)) {
             mbar_wait(landed_bar, landed_parity);
             landed_parity ^= 1;
         }
+        uint4 v[S::PAIRS][K];                    // all loads first: their latency overlaps instead of adding up per pair
 #pragma unroll
         for (int q = 0; q < S::PAIRS; q++) {
             const uint4 *row = reinterpret_cast<const uint4 *>(sIn + (q * 256 + 2 * tid) * K);
-            uint4 v[K];
+#pragma unroll
+            for (int i = 0; i < K; i++) v[q][i] = row[i];
+        }
+#pragma unroll
+        for (int q = 0; q < S::PAIRS; q++) {
             uint32_t sign = 0;
 #pragma unroll
-            for (int i = 0; i < K; i++) {
-                v[i] = row[i];
-                sign |= v[i].y | v[i].w;
-            }
+            for (int i = 0; i < K; i++) sign |= v[q][i].y | v[q][i].w;
             if ((int32_t)sign < 0) {
 #pragma unroll
                 for (int i = 0; i < K; i++) {
-                    canon_pair2(v[i].x, v[i].y);
-                    canon_pair2(v[i].z, v[i].w);
+                    canon_pair2(v[q][i].x, v[q][i].y);
+                    canon_pair2(v[q][i].z, v[q][i].w);
                 }
             }
             uint8_t *te = sS + (2 * q) * S::S_TILE + (tid >> 3) * S::SBO_S + (tid & 7) * 16;
 #pragma unroll
             for (int c = 0; c < S::SC; c++) {
-                *reinterpret_cast<uint4 *>(te + c * LBO) = v[c];                          // E: words 0 .. SC-1
-                *reinterpret_cast<uint4 *>(te + S::S_TILE + c * LBO) = v[K - S::SC + c];  // O: words K-SC .. K-1
+                *reinterpret_cast<uint4 *>(te + c * LBO) = v[q][c];                          // E: words 0 .. SC-1
+                *reinterpret_cast<uint4 *>(te + S::S_TILE + c * LBO) = v[q][K - S::SC + c];  // O: words K-SC .. K-1
             }
         }
         // rows complete: the secrets just written and the draws written during the previous pass
@@ -407,13 +448,6 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_cur = d_base + buf * S::D_BYTES;
-        // this CTA's next unit
-        uint32_t pn = p + step_p, un = u + step_u;
-        if (un >= unit_end) {
-            un -= units_per_p;
-            pn++;
-        }
-        const bool more = unit + gridDim.x < units_total;
         if (warp == 0) {
             if (elect_one()) {
                 issue_tile2<S>(taddr, d_cur, s_base, b_base);
@@ -427,17 +461,17 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
 
         // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
         if (more) {
-            stage_draws2<S, ROUNDS>(keys, pres, pn, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
+            stage_draws2<S, ROUNDS>(knext, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
             if (!by_bulk(un)) fill_secrets2<S, K>(secrets, ld, dim, pn, un, tid, sIn);
         }
 
         // ---- per pair: D = A . B^T on the tensor core, then compose the shares of batches 2 tid and 2 tid + 1 ------
         // share row 0 of this thread's first pair of the pass
-        char *optr = reinterpret_cast<char *>(out + (size_t)p * N * B + (size_t)u * S::PASS + 2 * tid);
+        char *optr = opass;
         const bool all_live = u < full_out_units;                             // every batch of the pass is below B
         const size_t row_bytes = B * 8u;
         const size_t pass_first = (size_t)u * S::PASS;
-#pragma unroll 1
+#pragma unroll
         for (int q = 0; q < S::PAIRS; q++) {
             uint64_t re[N];
             // batches of this thread that exist: 2 (both), 1 (only the even one) or 0
@@ -456,7 +490,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     tmem_ld_shares<N>(my_taddr, d);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j]);
+                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j], two16);
                 }
                 uint32_t d[N][8];
                 tmem_ld_shares<N>(my_taddr + S::ACC_COLS, d);
@@ -477,7 +511,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     }
                     dparity ^= 1;
                 }
-                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live);
+                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live, two16);
                 optr += 256 * 8;
             } else {
                 // one accumulator: E, then O into the same columns while E is being composed
@@ -501,7 +535,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     }
                     dparity ^= 1;
 #pragma unroll
-                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j]);
+                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j], two16);
                 }
                 mbar_wait(full_bar, parity);
                 parity ^= 1;
@@ -523,12 +557,14 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     }
                     dparity ^= 1;
                 }
-                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live);
+                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live, two16);
                 optr += 256 * 8;
             }
         }
         // every thread is past its TMEM loads of the last pair and every MMA of this pass has completed
         // (`full` was waited on), so the next pass may overwrite the secrets and reuse TMEM
+        // the same address for the next unit, by the difference (64-bit multiplies stay out of the loop)
+        opass += (un < u ? wrap_bytes : 0) + step_bytes;
         p = pn;
         u = un;
         buf ^= 1;
@@ -603,7 +639,7 @@ cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size
     kern<<<(unsigned)grid, CTA2, smem, lc.stream>>>(secrets, ld, dim, B, (uint32_t)unit_begin, (uint32_t)units_per_p,
                                                     (uint32_t)units_total, (uint32_t)std::min<size_t>(full_in, 0xffffffffu),
                                                     (uint32_t)std::min<size_t>(full_out, 0xffffffffu), keys, pres,
-                                                    reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok);
+                                                    reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok, 65536u);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }

@@ -7,7 +7,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${tag}_pytest.log 2
 tail -5 gpurun_out/${tag}_pytest.log
 for path in auto tc1 auto tc1; do
   for r in 20 12; do
-    timeout 300 python bench.py --steps 10 --warmup 3 --rounds $r --packed-path $path --no-e2e --no-cpu-baseline --no-round-sweep \
+    timeout 300 python bench.py --steps 10 --warmup 3 --rounds $r --packed-path $path --no-e2e --no-cpu-baseline --no-round-sweep --no-configs45 \
       > gpurun_out/${tag}_${path}_r${r}.json 2> gpurun_out/${tag}_${path}_r${r}.err
     python - <<PY
 import json
