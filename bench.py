@@ -395,6 +395,28 @@ def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
                     "8192 participants on 8 GPUs, fewer GPUs run the same 1024 participants per GPU (weak scaling)"}
 
 
+def pin_to_gpu_cores(torch, local, world):
+    """Keep this rank's host threads on the cores next to its GPU (the PCIe root's local_cpulist), and when several ranks
+    share that list give each its own share of it: the host side of the e2e leg is memcpy and DMA submission."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        cpus = []
+        for part in open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        if world > 1 and len(allowed) >= 2 * world:
+            per = len(allowed) // world
+            allowed = allowed[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, allowed)
+        return f"{allowed[0]}-{allowed[-1]} ({len(allowed)} cpus)"
+    except Exception:
+        return None
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -436,6 +458,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: sda_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity = pin_to_gpu_cores(torch, local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -611,36 +634,94 @@ def run_ours(args):
     value = world * T * dim * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host-buffer C-ABI calls, copies inside the timed region ----------------------------
+    # The calls a Rust shim would make, on host vectors: sda_share_generate per participant, sda_share_combine_rows per
+    # clerk.  One call is PCIe work (80 MB in, 133 MB out around a 50 us kernel); the library's concurrency model is one
+    # context per client thread, so the leg runs `--e2e-threads` client threads, each with its own context (own streams and
+    # device buffers): while one thread's call is still copying shares out, the next thread's call is copying secrets in,
+    # and both directions of the link stay busy.  Timed for at least a second; pinned buffers (sda_host_alloc) are the
+    # headline, ordinary pageable numpy arrays are reported beside it.
     Te = 0 if args.no_e2e else args.e2e_participants
-    e2e_value = None
+    e2e_value = e2e_pageable = pcie = None
+    e2e_steps = 0
     if Te > 0:
+        from concurrent.futures import ThreadPoolExecutor
+        nthreads = max(1, args.e2e_threads)
+        workers = [sda_b200.Context(local, rng_rounds=args.rounds) for _ in range(nthreads)]
+        for w in workers:
+            w.set_packed_path({"auto": 0, "cuda": 1, "tc": 2, "tc1": 3}[args.packed_path])
+        pool = ThreadPoolExecutor(nthreads)
         h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
         h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
         h_out = ctx.pinned_empty(n * B).reshape(n, B)
         for i in range(Te):
             h_sec[i][:] = d_sec[i].cpu().numpy()
 
-        def e2e_step(i):
+        def run_step(i, sec, sh, out):
             seeds = seeds_for(1000 + i, rank, Te)
-            for q in range(Te):
-                ctx.share_generate(scheme, h_sec[q], seeds[32 * q:32 * q + 32], out=h_sh[q])
-            for cl in range(n):
+
+            def gen(q):
+                workers[q % nthreads].share_generate(scheme, sec[q], seeds[32 * q:32 * q + 32], out=sh[q])
+
+            def comb(cl):
                 # the clerk receives its column of every participation (server snapshot transpose,
                 # snapshot.rs:11-27): a `Vec<Vec<Share>>` of P rows, passed as row pointers
-                ctx.share_combine(scheme, [h_sh[q, cl] for q in range(Te)], out=h_out[cl])
+                workers[cl % nthreads].share_combine(scheme, [sh[q, cl] for q in range(Te)], out=out[cl])
+            list(pool.map(gen, range(Te)))
+            list(pool.map(comb, range(n)))
 
-        e2e_step(-1)
+        run_step(-1, h_sec, h_sh, h_out)
+        run_step(-2, h_sec, h_sh, h_out)
         if world > 1:
             dist.barrier()
-        e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            e2e_step(i)
+        while e2e_steps < 3 or time.perf_counter() - t0 < 1.0:
+            run_step(e2e_steps, h_sec, h_sh, h_out)
+            e2e_steps += 1
         e2e_s = time.perf_counter() - t0
-        t_e = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        t_e = torch.tensor([e2e_s / e2e_steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e_value = world * Te * dim * e2e_steps / float(t_e.item())
+        e2e_value = world * Te * dim / float(t_e.item())
+        # the same calls on pageable memory (what a plain Vec<i64> is): staged through pinned bounce buffers inside the library
+        p_sec = [np.array(h) for h in h_sec]
+        p_sh = np.empty((Te, n, B), dtype=np.int64)
+        p_out = np.empty((n, B), dtype=np.int64)
+        run_step(-3, p_sec, p_sh, p_out)
+        t0 = time.perf_counter()
+        run_step(-4, p_sec, p_sh, p_out)
+        t_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
+        e2e_pageable = world * Te * dim / float(t_p.item())
+        if not np.array_equal(p_out, h_out) and rank == 0:
+            raise SystemExit("bench self-check failed: pageable and pinned host paths disagree")
+        # what the link itself gives this rank (pinned, 256 MB each way, alone and both ways at once)
+        hb = torch.empty(32 << 20, dtype=torch.int64).pin_memory()
+        hb2 = torch.empty(32 << 20, dtype=torch.int64).pin_memory()
+        db, db2 = torch.empty_like(hb, device="cuda"), torch.empty_like(hb, device="cuda")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def link(up, down):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(4):
+                if up:
+                    with torch.cuda.stream(s1):
+                        db.copy_(hb, non_blocking=True)
+                if down:
+                    with torch.cuda.stream(s2):
+                        hb2.copy_(db2, non_blocking=True)
+            torch.cuda.synchronize()
+            return 4 * hb.numel() * 8 / (time.perf_counter() - t0) / 1e9
+        link(True, True)
+        if world > 1:
+            dist.barrier()
+        pcie = {"h2d_GBps": link(True, False), "d2h_GBps": link(False, True), "duplex_each_way_GBps": link(True, True),
+                "note": "pinned 256 MB copies on this rank, all ranks at the same time"}
+        del hb, hb2, db, db2
+        pool.shutdown()
+        for w in workers:
+            w.close()
     h2d = Te * dim * 8 + n * Te * B * 8
     d2h = Te * n * B * 8 + n * B * 8
 
@@ -711,7 +792,12 @@ def run_ours(args):
                  if "tcgen05" in kernel_name else "u64 (Z_p, p=2^61-1): 32x32->64 IMAD limbs", "data": "synthetic",
         "config": workload_config(args, world), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "participants_per_step": Te, "api": "sda_share_generate per participant + sda_share_combine_rows per clerk (pinned host buffers)"},
+                "participants_per_step": Te, "steps_timed": e2e_steps, "client_threads": args.e2e_threads,
+                "pageable_value": e2e_pageable, "link": pcie, "cpu_affinity": affinity,
+                "link_bound": (None if not pcie else
+                               world * Te * dim / max(h2d / (pcie["duplex_each_way_GBps"] * 1e9), d2h / (pcie["duplex_each_way_GBps"] * 1e9))),
+                "api": "sda_share_generate per participant + sda_share_combine_rows per clerk (pinned host buffers; one context "
+                       "per client thread)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     json_out.write(json.dumps(line) + "\n")
@@ -733,6 +819,7 @@ def main():
                     help="share-gen kernel: tcgen05 byte-limb GEMM (auto/tc: paired tiles, tc1: first generation) or the "
                          "IMAD.WIDE CUDA-core kernel")
     ap.add_argument("--e2e-participants", type=int, default=4)
+    ap.add_argument("--e2e-threads", type=int, default=3, help="client threads (one context each) of the host-buffer leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

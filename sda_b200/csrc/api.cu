@@ -83,11 +83,12 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image;
+    DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image, tcg_image;
     int packed_path = SDA_PACKED_PATH_AUTO;
     bool debug_force_reject = false;   // SDA_B200_DEBUG_FORCE_REJECT=1 at context creation: treat the fused kernel's flag as set
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
     std::vector<uint64_t> tc2_image_key;  // likewise for the paired-tile kernel's two images (packed_tc2.cu)
+    std::vector<uint64_t> tcg_image_key;  // ... and for the run-time-shaped kernel (packed_tcg.cu)
     std::vector<uint64_t> tc_image_r_key; // (k, m', R) likewise for the reconstruction operand
     std::vector<uint64_t> r_key;          // (scheme, clerk subset) of r_cached
     Matrix r_cached;
@@ -230,6 +231,23 @@ int validate(sda_ctx *ctx, const sda_sharing_scheme *s, Packed *pk) {
                 if (pk->a[i] == pk->a[l])
                     return fail(ctx, SDA_ERR_INVALID, "omega_secrets has order <= secret_count + privacy_threshold: "
                                                       "interpolation points collide");
+        // tss 0.2 evaluates through a radix-2 inverse FFT over k + t + 1 points and a radix-3 FFT over n + 1 points.  When
+        // the sizes are FFT sizes the reference computes THAT transform whatever the roots are: only primitive roots of
+        // exactly those orders make it the interpolation this library evaluates, so anything else is refused instead of
+        // silently producing a different map.  (Other sizes cannot run in tss at all; they are this library's extension.)
+        const uint64_t m2 = k + t + 1, m3 = n + 1;
+        auto is_pow = [](uint64_t v, uint64_t b) {
+            while (v % b == 0) v /= b;
+            return v == 1;
+        };
+        if (is_pow(m2, 2) && is_pow(m3, 3) && m2 <= m3) {
+            if (powmod_h(ws, m2, p) != 1 || (m2 > 1 && powmod_h(ws, m2 / 2, p) == 1))
+                return fail(ctx, SDA_ERR_INVALID, "omega_secrets is not a primitive %llu-th root of unity: tss 0.2 would run its "
+                                                  "radix-2 FFT with it and share a different polynomial", (unsigned long long)m2);
+            if (powmod_h(wh, m3, p) != 1 || (m3 > 1 && powmod_h(wh, m3 / 3, p) == 1))
+                return fail(ctx, SDA_ERR_INVALID, "omega_shares is not a primitive %llu-th root of unity: tss 0.2 would run its "
+                                                  "radix-3 FFT with it and evaluate at different points", (unsigned long long)m3);
+        }
         for (size_t i = 0; i < pk->b.size(); i++) {
             if (pk->b[i] == 1) return fail(ctx, SDA_ERR_INVALID, "omega_shares has order <= share_count: share point equals 1");
             for (size_t l = 0; l < i; l++)
@@ -473,40 +491,66 @@ int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
     return SDA_OK;
 }
 
-// Tensor-core share generation, whichever kernel serves the scheme: the paired-tile kernel (packed_tc2.cu) for
-// 2^61 - 1 when the vector fits its 32-bit row offsets, packed_tc.cu otherwise (any prime; or when the context asks
-// for it with SDA_PACKED_PATH_TENSOR_CORES_V1).  Both generate batches first_batch .. first_batch + n_batches - 1 of
-// every participant; first_batch is a multiple of share_tc_slice_batches().
-bool use_tc2(const sda_ctx *ctx, const Packed &pk, size_t dim) {
-    return pk.p == P61 && ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 && packed_share_tc2_supported(pk.k, pk.t, pk.n, dim);
+// Tensor-core share generation, whichever kernel serves the scheme: the paired-tile kernel (packed_tc2.cu) for the
+// instantiated shapes over 2^61 - 1 when the vector fits its 32-bit row offsets, packed_tc.cu for those shapes over
+// other primes (or when the context asks for it with SDA_PACKED_PATH_TENSOR_CORES_V1), and the run-time-shaped kernel
+// (packed_tcg.cu) for every other (k, t, n).  All generate batches first_batch .. first_batch + n_batches - 1 of every
+// participant; first_batch is a multiple of share_tc_slice_batches().
+enum { TC_NONE = 0, TC_V1 = 1, TC_PAIRED = 2, TC_RUNTIME = 3 };
+int tc_kernel_for(const sda_ctx *ctx, const Packed &pk, size_t dim) {
+    if (ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES) return TC_NONE;
+    if (packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
+        if (pk.p == P61 && ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 && packed_share_tc2_supported(pk.k, pk.t, pk.n, dim))
+            return TC_PAIRED;
+        return TC_V1;
+    }
+    return packed_share_tcg_supported(pk.k, pk.t, pk.n) ? TC_RUNTIME : TC_NONE;
 }
 size_t share_tc_slice_batches(const sda_ctx *ctx, const Packed &pk, size_t dim) {
-    return use_tc2(ctx, pk, dim) ? packed_share_tc2_slice_batches(pk.k, pk.t, pk.n) : packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
+    switch (tc_kernel_for(ctx, pk, dim)) {
+    case TC_PAIRED: return packed_share_tc2_slice_batches(pk.k, pk.t, pk.n);
+    case TC_V1: return packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
+    case TC_RUNTIME: return packed_share_tcg_slice_batches(pk.k, pk.t, pk.n);
+    }
+    return 0;
+}
+// the constant GEMM operand of kernel `which`, resident on the device per (kernel, scheme)
+int ensure_image(sda_ctx *ctx, int which, const Packed &pk, const Matrix &M, DevBuf *buf, std::vector<uint64_t> *cached) {
+    std::vector<uint64_t> key{(uint64_t)which, (uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
+    key.insert(key.end(), M.e, M.e + M.rows * M.cols);
+    if (key == *cached) return SDA_OK;
+    const size_t ib = which == TC_PAIRED ? packed_share_tc2_image_bytes(pk.k, pk.t, pk.n) : packed_share_tcg_image_bytes(pk.k, pk.t, pk.n);
+    std::vector<uint8_t> img(ib);
+    if (which == TC_PAIRED) packed_share_tc2_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
+    else packed_share_tcg_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
+    CU(buf->reserve(ib));
+    CU(cudaMemcpyAsync(buf->p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
+    *cached = key;
+    return SDA_OK;
 }
 int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const FieldParams &f, const DrawParams &dr,
                     const int64_t *d_secrets, size_t ld, size_t P, size_t dim, size_t first_batch, size_t n_batches,
                     const ChaChaKey *d_keys, int64_t *d_out) {
-    if (!use_tc2(ctx, pk, dim)) {
+    switch (tc_kernel_for(ctx, pk, dim)) {
+    case TC_V1:
         OK(ensure_tc_image(ctx, pk, M));
         CU(launch_packed_share_tc(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches,
                                   d_keys, (const uint8_t *)ctx->tc_image.p, d_out, ctx->d_flag));
         return SDA_OK;
+    case TC_PAIRED:
+        OK(ensure_image(ctx, TC_PAIRED, pk, M, &ctx->tc2_image, &ctx->tc2_image_key));
+        CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
+        CU(launch_packed_share_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
+                                   (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
+        return SDA_OK;
+    case TC_RUNTIME:
+        OK(ensure_image(ctx, TC_RUNTIME, pk, M, &ctx->tcg_image, &ctx->tcg_image_key));
+        CU(launch_packed_share_tcg(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches,
+                                   d_keys, (const uint8_t *)ctx->tcg_image.p, d_out, ctx->d_flag));
+        return SDA_OK;
     }
-    const size_t ib = packed_share_tc2_image_bytes(pk.k, pk.t, pk.n);
-    std::vector<uint64_t> key{(uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
-    key.insert(key.end(), M.e, M.e + M.rows * M.cols);
-    if (key != ctx->tc2_image_key) {
-        std::vector<uint8_t> img(ib);
-        packed_share_tc2_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
-        CU(ctx->tc2_image.reserve(ib));
-        CU(cudaMemcpyAsync(ctx->tc2_image.p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));   // img goes out of scope
-        ctx->tc2_image_key = key;
-    }
-    CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
-    CU(launch_packed_share_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
-                               (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
-    return SDA_OK;
+    return fail(ctx, SDA_ERR_UNSUPPORTED, "no tensor-core kernel for this scheme");
 }
 
 // ---- core device-side operations (shared by host and device entry points) --------------------
@@ -538,9 +582,8 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
     const ChaChaKey *d_keys = (const ChaChaKey *)ctx->keys.p;
     const bool fast = additive ? (n == 1 || additive_split_has_fast_path(n)) : packed_share_has_fast_path(pk.k, pk.t, pk.n);
     bool exact = !fast;
-    // instantiated shapes, any prime: tensor-core kernel unless the context asks for the CUDA-core one
-    const bool use_tc = !additive && fast && ctx->packed_path != SDA_PACKED_PATH_CUDA_CORES &&
-                        packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0;
+    // any shape, any prime: a tensor-core kernel unless the context asks for the CUDA-core ones
+    const bool use_tc = !additive && tc_kernel_for(ctx, pk, dim) != TC_NONE;
     if (use_tc) {
         OK(clear_flags(ctx));
         OK(launch_share_tc(ctx, pk, M, f, dr, d_secrets, ld, P, dim, 0, B, d_keys, d_out));
@@ -906,7 +949,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     // goes back to the allocator
     for (DevBuf *b : {&ctx->keys, &ctx->keys_pre, &ctx->draws})
         if (b->p) cudaMemset(b->p, 0, b->cap);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image}) b->release();
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image, &ctx->tcg_image}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);

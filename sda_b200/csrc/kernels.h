@@ -107,6 +107,15 @@ size_t packed_share_tc2_key_scratch_bytes(size_t P);
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
                                     uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
+// the run-time-shaped kernel (packed_tcg.cu): any k + t <= 16, n <= 32, t >= 1, any prime; same slicing contract
+bool packed_share_tcg_supported(int k, int t, int n);
+size_t packed_share_tcg_image_bytes(int k, int t, int n);
+void packed_share_tcg_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img);
+size_t packed_share_tcg_slice_batches(int k, int t, int n);
+cudaError_t launch_packed_share_tcg(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int k, int t,
+                                    int n, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
+                                    size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *shares_out,
+                                    unsigned *flag);
 // fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,

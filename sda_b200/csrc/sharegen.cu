@@ -115,7 +115,49 @@ additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim
     if (rej) atomicOr(flag, 1u);
 }
 
-// any n, draws read from memory (exact path and n - 1 > 4): one element per thread
+// additive split for ANY share count, in-kernel randomness (additive.rs:32-51 with n - 1 = D a run-time value): a thread
+// owns 8 adjacent elements, i.e. exactly D whole keystream blocks (draw q = e D + j of the participant's stream is share j
+// of element e).  The running "secret - sum of draws" of the 8 elements lives in shared memory ([element][thread], conflict
+// free) because the element a draw belongs to is a run-time index; shares are stored as they are drawn.
+template <bool M61, uint32_t DK, int ROUNDS>
+__global__ void __launch_bounds__(CTA)
+additive_split_any_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, int D, const ChaChaKey *__restrict__ keys,
+                          int64_t *__restrict__ out, FieldParams f, DrawParams dr, unsigned *flag) {
+    __shared__ uint64_t acc[8][CTA];
+    const size_t p = blockIdx.y;
+    const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
+    const size_t e0 = u * 8;
+    if (e0 >= dim) return;
+    const int nvalid = (int)min((size_t)8, dim - e0);
+    const ChaChaKey key = load_key(keys, p);
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e][threadIdx.x] = e < nvalid ? canon<M61>(f, secrets[p * ld + e0 + e]) : 0;
+    int64_t *o = out + p * (size_t)(D + 1) * dim + e0;
+    bool rej = false;
+    int e = 0, j = 0;
+    for (int b = 0; b < D; b++) {
+        uint64_t blk[8];
+        chacha_draws8<ROUNDS>(key, u * (size_t)D + b, blk);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            bool r;
+            const uint64_t s = draw_reduce<DK>(dr, blk[i], r);
+            if (e < nvalid) {
+                rej |= r;
+                o[(size_t)j * dim + e] = (int64_t)s;                            // additive.rs:42-44
+                acc[e][threadIdx.x] = submod(acc[e][threadIdx.x], s, f.m);      // additive.rs:47
+            }
+            if (++j == D) {
+                j = 0;
+                e++;
+            }
+        }
+    }
+    for (int k = 0; k < nvalid; k++) o[(size_t)D * dim + k] = (int64_t)acc[k][threadIdx.x];
+    if (rej) atomicOr(flag, 1u);
+}
+
+// any n, draws read from memory (exact path): one element per thread
 template <bool M61>
 __global__ void __launch_bounds__(CTA)
 additive_split_mem_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, int n,
@@ -446,7 +488,7 @@ bool packed_share_has_fast_path(int k, int t, int n) {
     return (k == 3 && t == 2 && n == 5) || (k == 5 && t == 4 && n == 9) || (k == 3 && t == 4 && n == 7) ||
            (k == 3 && t == 4 && n == 8);
 }
-bool additive_split_has_fast_path(int n) { return n >= 2 && n <= 5; }
+bool additive_split_has_fast_path(int n) { return n >= 2; }   // n <= 5: unrolled kernel; above: the run-time one
 
 cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int n,
                                   const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
@@ -462,6 +504,25 @@ cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, con
         case 3: return additive_dispatch<3>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
         case 4: return additive_dispatch<4>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
         }
+    }
+    if (draws == nullptr && n > 5) {
+        const bool m61 = f.kind == FIELD_MERSENNE61;
+        *lc.kernel_name = m61 ? "additive_split<in-kernel rng, run-time share count>/mersenne61"
+                              : "additive_split<in-kernel rng, run-time share count>/generic";
+        dim3 grid((unsigned)(((dim + 7) / 8 + CTA - 1) / CTA), (unsigned)P);
+#define SDA_AA(M61, DK, R) additive_split_any_kernel<M61, DK, R><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, n - 1, keys, shares_out, f, dr, flag)
+        if (m61) {
+            if (rounds == 8) SDA_AA(true, DRAW_M61, 8);
+            else if (rounds == 12) SDA_AA(true, DRAW_M61, 12);
+            else SDA_AA(true, DRAW_M61, 20);
+        } else {
+            if (rounds == 8) SDA_AA(false, DRAW_GENERIC, 8);
+            else if (rounds == 12) SDA_AA(false, DRAW_GENERIC, 12);
+            else SDA_AA(false, DRAW_GENERIC, 20);
+        }
+#undef SDA_AA
+        ++*lc.nlaunch;
+        return cudaGetLastError();
     }
     if (draws == nullptr && n > 1) return cudaErrorInvalidValue;   // caller must pre-draw
     *lc.kernel_name = "additive_split<draws from memory>";

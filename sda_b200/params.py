@@ -20,6 +20,8 @@ P61_GENERIC = 2305843009213693921   # largest prime below 2^61 - 1 - 30; checked
 ROOT_ORDER_7 = 69203453413471971
 ROOT_ORDER_11 = 54008984094220448
 ROOT_ORDER_13 = 844735144842896729
+ROOT_ORDER_31 = 484083891529811867   # for shapes beyond the BASELINE ones (k + t + 1 <= 31, n + 1 <= 41)
+ROOT_ORDER_41 = 439424789145975530
 
 # the reference's own packed-Shamir test parameters (full_loop.rs:57-64)
 REFERENCE_TEST = dict(secret_count=3, share_count=8, privacy_threshold=4, prime_modulus=433,

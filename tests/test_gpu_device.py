@@ -68,6 +68,34 @@ def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
         ctx.set_packed_path(0)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 6), (7, 5, 16), (1, 1, 2), (4, 1, 9), (9, 7, 32)])
+@pytest.mark.parametrize("p", [P61, params.P61_GENERIC])
+def test_runtime_shaped_kernel_many_participants(ctx, oracle, torch_cuda, shape, p):
+    """packed_tcg.cu on device buffers: several participants, vectors spanning many passes and ending inside one,
+    strided rows, negative secrets -- every share against the oracle"""
+    t = torch_cuda
+    k, tt, n = shape
+    try:
+        s = util.packed_scheme(p, k, tt, n, oracle)
+    except StopIteration:
+        pytest.skip("no suitable prime orders in p-1")
+    rng = np.random.default_rng(k * 100 + n)
+    for P, dim, ld in [(1, 1, 1), (3, 256 * k * 3 + 1, 256 * k * 3 + 4), (2, 40000, 40000), (5, 256 * k, 256 * k + 2)]:
+        B = s.batches(dim)
+        secrets = np.zeros((P, ld), dtype=np.int64)
+        secrets[:, :dim] = rng.integers(0, p, size=(P, dim), dtype=np.int64)
+        secrets[0, :dim:9] = rng.integers(-(1 << 63), 1 << 63, size=secrets[0, :dim:9].shape, dtype=np.int64)
+        seeds = b"".join(util.seed_bytes(f"tcg/{shape}/{P}/{dim}/{pi}") for pi in range(P))
+        d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_dev(s, dev(t, secrets), ld, P, dim, seeds, d_out)
+        ctx.synchronize()
+        assert "run-time shape" in ctx.last_kernel() and "tcgen05" in ctx.last_kernel()
+        got = host(d_out)
+        for pi in range(P):
+            exp = util.oracle_generate(oracle, s, secrets[pi, :dim], seeds[32 * pi:32 * pi + 32], matrix=True)
+            assert np.array_equal(got[pi], util.canon(oracle, p, exp)), (shape, P, dim, pi)
+
+
 @pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
 @pytest.mark.parametrize("offset,ld_pad", [(0, 0), (1, 0), (0, 1), (1, 1), (2, 2)])
 def test_packed_tc_secret_sources_of_every_alignment(ctx, oracle, torch_cuda, mk, offset, ld_pad):

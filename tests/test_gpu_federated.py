@@ -52,7 +52,7 @@ def test_fixed_point_codec_matches_oracle(ctx, oracle):
 
 def test_federated_round_trip(ctx, oracle):
     import torch as t
-    s = sda_b200.LinearSecretSharingScheme.PackedShamir(3, 8, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
+    s = sda_b200.LinearSecretSharingScheme.PackedShamir(3, 9, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)   # n + 1 = 10: not an FFT size
     n, k = s.output_size(), s.input_size()
     P, dim = 37, 5000
     B = s.batches(dim)
@@ -89,7 +89,7 @@ def test_federated_round_trip(ctx, oracle):
     ctx.synchronize()
     assert t.equal(d_sums, d_fused)
 
-    # recipient: clerk 2 never answered; reveal from the other seven, combine the mask seeds, unmask, decode the mean
+    # recipient: clerks 2 and 8 never answered; reveal from the other seven, combine the mask seeds, unmask, decode the mean
     idx = [0, 1, 3, 4, 5, 6, 7]
     got = ctx.secret_reconstruct(s, dim, [(i, d_sums[i].cpu().numpy()) for i in idx])
     assert np.array_equal(got, masked.astype(object).sum(axis=0) % P61)

@@ -99,7 +99,7 @@ DIMS = [1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 127, 128, 129, 1000, 4099]
 
 
 @pytest.mark.parametrize("modulus", [433, P61, PGEN, 2, 1, M_MAX])
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 9])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 9, 16, 33])
 def test_additive_generate(ctx, oracle, n, modulus):
     s = LSS.Additive(n, modulus)
     rng = np.random.default_rng(n * 1000 + modulus % 997)
@@ -116,6 +116,8 @@ def test_additive_generate(ctx, oracle, n, modulus):
             got = ctx.share_generate(s, secrets, seed)
             assert got.shape == (n, dim)
             assert np.array_equal(got, exp), (n, modulus, dim, kind)
+    if n > 1 and modulus in (433, P61, PGEN):
+        assert "in-kernel rng" in ctx.last_kernel()      # no share count falls back to draws materialised in HBM
 
 
 @pytest.mark.parametrize("modulus", [M_REJECT, 3 << 61])
@@ -172,21 +174,25 @@ def test_packed_generate_literal_oracle(ctx, oracle):
         assert np.array_equal(ctx.share_generate(s, secrets, seed), exp)
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 3), (2, 3, 6), (4, 3, 10), (7, 5, 16), (2, 1, 4), (8, 8, 20)])
+@pytest.mark.parametrize("shape", [(1, 1, 3), (2, 3, 6), (4, 3, 10), (7, 5, 16), (2, 1, 4), (8, 8, 20), (15, 1, 17), (1, 15, 32),
+                                   (3, 3, 7), (6, 7, 14), (5, 2, 9)])
 @pytest.mark.parametrize("p", [P61, PGEN, 2305843009213693561])
 def test_packed_generate_generic_shapes(ctx, oracle, shape, p):
-    """shapes without an in-kernel-rng instantiation go through the exact-draw path"""
+    """any (k, t, n) the reference accepts (packed_shamir.rs:13-27) runs on the run-time-shaped tcgen05 kernel: odd t,
+    k + t up to 16, n up to 32 -- no scheme materialises its draws in HBM"""
     k, t, n = shape
     try:
         s = util.packed_scheme(p, k, t, n, oracle)
     except StopIteration:
         pytest.skip("no suitable prime orders in p-1")
     rng = np.random.default_rng(k + 10 * n)
-    for dim in [1, k, k + 1, 10 * k - 1, 1000]:
-        secrets = util.rand_secrets(rng, dim, p)
-        seed = util.seed_bytes(f"gen/{shape}/{dim}")
-        exp = util.oracle_generate(oracle, s, secrets, seed, matrix=True)
-        assert np.array_equal(ctx.share_generate(s, secrets, seed), exp), (shape, p, dim)
+    for dim in [1, k, k + 1, 10 * k - 1, 1000, 256 * k + 1, 3000 * k + 2]:
+        for kind in ("canonical", "signed"):
+            secrets = util.rand_secrets(rng, dim, p, kind)
+            seed = util.seed_bytes(f"gen/{shape}/{dim}/{kind}")
+            exp = util.oracle_generate(oracle, s, secrets, seed, matrix=True)
+            assert np.array_equal(ctx.share_generate(s, secrets, seed), exp), (shape, p, dim, kind)
+    assert "run-time shape" in ctx.last_kernel() and "tcgen05" in ctx.last_kernel()
 
 
 def test_packed_share_matrix_matches_oracle(ctx, oracle):
@@ -355,3 +361,10 @@ def test_scheme_validation(crypto):
     with pytest.raises(SdaClientError) as e:
         crypto.new_share_generator(LSS.PackedShamir(30, 60, 30, P61, 3, 5))
     assert e.value.code == 4
+    # FFT sizes (k + t + 1 = 2^a, n + 1 = 3^b) run tss 0.2's FFTs whatever the roots are: only primitive roots of exactly
+    # those orders make that the interpolation; 17 has order 27 mod 433, 151 has order 16 (354 = order 8, 150 = order 9)
+    with pytest.raises(SdaClientError, match="primitive 9-th root"):
+        crypto.new_share_generator(LSS.PackedShamir(3, 8, 4, 433, 354, 17))
+    with pytest.raises(SdaClientError, match="primitive 8-th root"):
+        crypto.new_share_generator(LSS.PackedShamir(3, 8, 4, 433, 151, 150))
+    crypto.new_share_generator(LSS.PackedShamir(3, 8, 4, 433, 354, 150))

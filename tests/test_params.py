@@ -14,7 +14,8 @@ def _order(O, w, p, limit=64):
 
 def test_roots_of_unity(oracle):
     p = params.P61
-    for q, w in ((7, params.ROOT_ORDER_7), (11, params.ROOT_ORDER_11), (13, params.ROOT_ORDER_13)):
+    for q, w in ((7, params.ROOT_ORDER_7), (11, params.ROOT_ORDER_11), (13, params.ROOT_ORDER_13),
+                 (31, params.ROOT_ORDER_31), (41, params.ROOT_ORDER_41)):
         assert oracle.find_root_of_order(p, q) == w
         assert _order(oracle, w, p) == q
 

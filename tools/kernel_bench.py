@@ -19,6 +19,7 @@ import torch  # noqa: E402
 
 import sda_b200  # noqa: E402
 from sda_b200 import LinearMaskingScheme as LMS  # noqa: E402
+from sda_b200 import LinearSecretSharingScheme as LSS  # noqa: E402
 from sda_b200 import params  # noqa: E402
 
 
@@ -146,14 +147,39 @@ def main():
         except Exception as e:                       # no suitable orders: skip the line
             print(json.dumps({"kernel": "packed_share generic prime", "skipped": str(e)}), flush=True)
 
-        # ---- reveal with a missing clerk: the reference's own test shape over the 61-bit prime --------------
-        s = params.LinearSecretSharingScheme.PackedShamir(3, 8, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
+        # ---- shapes without a templated kernel: the run-time-shaped tcgen05 kernel (packed_tcg.cu) ---------------------
+        for k_, t_, n_ in ((3, 2, 6), (3, 3, 7), (5, 4, 10), (8, 8, 20)):
+            s = params.LinearSecretSharingScheme.PackedShamir(k_, n_, t_, P61, params.ROOT_ORDER_31, params.ROOT_ORDER_41)
+            P, dim = 64, 10_000_000
+            B = s.batches(dim)
+            sec = empty(P, dim)
+            ctx.synth_fill_dev(10, P61, 0, P * dim, sec)
+            sh = empty(P, n_, B)
+            sd = seeds(f"rt{k_}{t_}{n_}", P)
+            timeit(f"packed_share k={k_} t={t_} n={n_} [{P}][10M] (run-time-shaped tensor-core kernel)",
+                   lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n_ * B) * 8,
+                   f"8(1+n/k) = {8 * (1 + n_ / k_):.2f} B per secret")
+            del sec, sh
+            torch.cuda.empty_cache()
+        # ---- additive split with a share count beyond the unrolled kernels (n = 9) ---------------------------------------
+        s9, P, dim = LSS.Additive(9, P61), 128, 1_000_000
+        sec = empty(P, dim)
+        ctx.synth_fill_dev(11, P61, 0, P * dim, sec)
+        sh = empty(P, 9, dim)
+        sd = seeds("add9", P)
+        timeit("additive_split n=9 [128][1M] (run-time share count)", lambda: ctx.share_generate_dev(s9, sec, dim, P, dim, sd, sh),
+               P * dim, P * dim * 8 * 10, "keystream-bound: 8 draws per element")
+        del sec, sh
+        torch.cuda.empty_cache()
+
+        # ---- reveal with two missing clerks (k=3, t=4, n=9 over the 61-bit prime) ---------------------------------------
+        s = params.LinearSecretSharingScheme.PackedShamir(3, 9, 4, P61, params.ROOT_ORDER_11, params.ROOT_ORDER_13)
         dim = 10_000_000
         B = s.batches(dim)
         rows = empty(7, B)
         ctx.synth_fill_dev(7, P61, 0, 7 * B, rows)
         rec = empty(dim)
-        timeit("packed_reconstruct k=3 t=4 n=8, clerks {0..5,7} x [3.33M] -> [10M]",
+        timeit("packed_reconstruct k=3 t=4 n=9, clerks {0..5,7} x [3.33M] -> [10M]",
                lambda: ctx.secret_reconstruct_dev(s, dim, [0, 1, 2, 3, 4, 5, 7], rows, B, 7, B, rec), dim, (7 * B + dim) * 8)
         del rows, rec
         torch.cuda.empty_cache()
