@@ -338,7 +338,6 @@ def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
 
     with torch.cuda.stream(stream):
         d_x = torch.empty((Pt, dim), dtype=torch.float32, device="cuda")
-        d_q = torch.empty((Pt, dim), dtype=torch.int64, device="cuda")
         d_m = torch.empty((Pt, dim), dtype=torch.int64, device="cuda")
         d_sum = torch.zeros((n, B), dtype=torch.int64, device="cuda")
         d_seedw = torch.zeros((P, words), dtype=torch.int64, device="cuda")
@@ -351,15 +350,14 @@ def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
             truth += d_x[:pt].sum(dim=0, dtype=torch.float64)
             stream.synchronize()
 
-            def encode_mask():
-                ctx.fixed_encode_dev(p, FRAC, d_x, pt * dim, d_q)
+            def encode_mask():     # one pass per participant: float -> fixed point -> + ChaCha mask (participate.rs:53-54)
                 for i in range(pt):
-                    ctx.mask_dev(ms_, d_q[i], dim, sd(f"fed/mask/{rank}/{t0 + i}"), d_seedw[t0 + i], d_m[i])
+                    ctx.fixed_encode_mask_dev(ms_, p, FRAC, d_x[i], dim, sd(f"fed/mask/{rank}/{t0 + i}"), d_seedw[t0 + i], d_m[i])
             timed("encode_mask", encode_mask)
             seeds = b"".join(sd(f"fed/share/{rank}/{t0 + i}") for i in range(pt))
             timed("share_gen_clerk_sum",
                   lambda: ctx.share_generate_combine_dev(scheme, d_m, dim, pt, dim, seeds, d_sum, d_acc_in=d_sum if t0 else None))
-        del d_x, d_q, d_m
+        del d_x, d_m
         d_mask = torch.empty(dim, dtype=torch.int64, device="cuda")
         timed("mask_expand", lambda: ctx.mask_combine_dev(ms_, d_seedw, P, words, d_mask))
 
@@ -651,49 +649,61 @@ def run_ours(args):
             w.set_packed_path({"auto": 0, "cuda": 1, "tc": 2, "tc1": 3}[args.packed_path])
         pool = ThreadPoolExecutor(nthreads)
         h_sec = [ctx.pinned_empty(dim) for _ in range(Te)]
-        h_sh = ctx.pinned_empty(Te * n * B).reshape(Te, n, B)
+        h_sh2 = [ctx.pinned_empty(Te * n * B).reshape(Te, n, B) for _ in range(2)]
         h_out = ctx.pinned_empty(n * B).reshape(n, B)
         for i in range(Te):
             h_sec[i][:] = d_sec[i].cpu().numpy()
 
-        def run_step(i, sec, sh, out):
+        def run_step(i, sec, sh_new, sh_prev, out):
+            """the participants of round i share (sda_share_generate, one call each) while the clerks sum the shares of
+            round i - 1 (sda_share_combine_rows, one call per clerk): the participants' calls are copy-out heavy, the clerks'
+            copy-in heavy, so the two kinds of client keep both directions of the link busy"""
             seeds = seeds_for(1000 + i, rank, Te)
 
             def gen(q):
-                workers[q % nthreads].share_generate(scheme, sec[q], seeds[32 * q:32 * q + 32], out=sh[q])
+                workers[q % nthreads].share_generate(scheme, sec[q], seeds[32 * q:32 * q + 32], out=sh_new[q])
 
             def comb(cl):
                 # the clerk receives its column of every participation (server snapshot transpose,
                 # snapshot.rs:11-27): a `Vec<Vec<Share>>` of P rows, passed as row pointers
-                workers[cl % nthreads].share_combine(scheme, [sh[q, cl] for q in range(Te)], out=out[cl])
-            list(pool.map(gen, range(Te)))
-            list(pool.map(comb, range(n)))
+                workers[(Te + cl) % nthreads].share_combine(scheme, [sh_prev[q, cl] for q in range(Te)], out=out[cl])
+            if args.e2e_mode == "phases":      # participants first, then the clerks (of the previous round's shares)
+                list(pool.map(gen, range(Te)))
+                if sh_prev is not None:
+                    list(pool.map(comb, range(n)))
+                return
+            futs = [pool.submit(gen, q) for q in range(Te)] + ([pool.submit(comb, cl) for cl in range(n)] if sh_prev is not None else [])
+            for f_ in futs:
+                f_.result()
 
-        run_step(-1, h_sec, h_sh, h_out)
-        run_step(-2, h_sec, h_sh, h_out)
+        run_step(-1, h_sec, h_sh2[1], None, h_out)
+        run_step(-2, h_sec, h_sh2[0], h_sh2[1], h_out)
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         while e2e_steps < 3 or time.perf_counter() - t0 < 1.0:
-            run_step(e2e_steps, h_sec, h_sh, h_out)
+            run_step(e2e_steps, h_sec, h_sh2[(e2e_steps + 1) % 2], h_sh2[e2e_steps % 2], h_out)
             e2e_steps += 1
         e2e_s = time.perf_counter() - t0
         t_e = torch.tensor([e2e_s / e2e_steps], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
         e2e_value = world * Te * dim / float(t_e.item())
+        # what the last timed step combined: the shares generated by the step before it
+        last_prev = h_sh2[(e2e_steps - 1) % 2]
         # the same calls on pageable memory (what a plain Vec<i64> is): staged through pinned bounce buffers inside the library
         p_sec = [np.array(h) for h in h_sec]
+        p_prev = np.array(last_prev)
         p_sh = np.empty((Te, n, B), dtype=np.int64)
         p_out = np.empty((n, B), dtype=np.int64)
-        run_step(-3, p_sec, p_sh, p_out)
+        run_step(-3, p_sec, p_sh, p_prev, p_out)
         t0 = time.perf_counter()
-        run_step(-4, p_sec, p_sh, p_out)
+        run_step(-4, p_sec, p_sh, p_prev, p_out)
         t_p = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t_p, op=dist.ReduceOp.MAX)
         e2e_pageable = world * Te * dim / float(t_p.item())
-        if not np.array_equal(p_out, h_out) and rank == 0:
+        if not np.array_equal(p_out, h_out) and rank == 0:      # both summed the same shares
             raise SystemExit("bench self-check failed: pageable and pinned host paths disagree")
         # what the link itself gives this rank (pinned, 256 MB each way, alone and both ways at once)
         hb = torch.empty(32 << 20, dtype=torch.int64).pin_memory()
@@ -792,7 +802,7 @@ def run_ours(args):
                  if "tcgen05" in kernel_name else "u64 (Z_p, p=2^61-1): 32x32->64 IMAD limbs", "data": "synthetic",
         "config": workload_config(args, world), "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "participants_per_step": Te, "steps_timed": e2e_steps, "client_threads": args.e2e_threads,
+                "participants_per_step": Te, "steps_timed": e2e_steps, "client_threads": args.e2e_threads, "mode": args.e2e_mode,
                 "pageable_value": e2e_pageable, "link": pcie, "cpu_affinity": affinity,
                 "link_bound": (None if not pcie else
                                world * Te * dim / max(h2d / (pcie["duplex_each_way_GBps"] * 1e9), d2h / (pcie["duplex_each_way_GBps"] * 1e9))),
@@ -819,7 +829,9 @@ def main():
                     help="share-gen kernel: tcgen05 byte-limb GEMM (auto/tc: paired tiles, tc1: first generation) or the "
                          "IMAD.WIDE CUDA-core kernel")
     ap.add_argument("--e2e-participants", type=int, default=4)
-    ap.add_argument("--e2e-threads", type=int, default=3, help="client threads (one context each) of the host-buffer leg")
+    ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "phases"],
+                    help="host-buffer leg: clerks of round i-1 concurrently with the participants of round i, or one after the other")
+    ap.add_argument("--e2e-threads", type=int, default=4, help="client threads (one context each) of the host-buffer leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")

@@ -271,6 +271,18 @@ int sda_varint_decode(sda_ctx *ctx, const uint8_t *buf, size_t len, int64_t *sha
 int sda_varint_encode_dev(sda_ctx *ctx, const int64_t *d_shares, size_t n, uint8_t *d_out, size_t *out_len);
 int sda_varint_decode_dev(sda_ctx *ctx, const uint8_t *d_buf, size_t len, int64_t *d_shares_out, size_t cap, size_t *n);
 
+/* ---- server snapshot transpose: the layout producer of the clerk's matrix --------------------------- */
+/* server/src/snapshot.rs:11-27 -> stores.rs:86-101 (iter_snapshot_clerk_jobs_data): every participation holds one
+ * encrypted share vector per clerk; a snapshot regroups them into one job per clerk.  Here the blobs are byte strings
+ * concatenated in device memory: blob (p, c) of d_blobs is bytes [offsets[p n + c], offsets[p n + c + 1]) (P n + 1
+ * offsets, HOST memory, participation-major); d_out receives clerk 0's P blobs, then clerk 1's, ... and
+ * out_offsets[c P + p] (P n + 1 entries, HOST, filled by the call) says where blob (p, c) went.  d_out needs
+ * offsets[P n] - offsets[0] bytes.  Byte-exact data movement; which bytes they are (sealed boxes, varints, raw i64
+ * rows) is the caller's business.  With equal-length raw rows the clerk's rows need no transpose at all:
+ * sda_share_combine_dev takes the strided view shares[:, c, :] directly. */
+int sda_snapshot_transpose_dev(sda_ctx *ctx, const uint8_t *d_blobs, const uint64_t *offsets, size_t P, size_t n,
+                               uint8_t *d_out, uint64_t *out_offsets);
+
 /* ---- fixed-point codec for real-valued vectors (model updates) -------------------------------- */
 /* Not in the reference, whose API takes Vec<i64> (client/src/participate.rs:10,25): the adjacent step
  * BASELINE config #5 needs.  encode: rint(x * 2^frac_bits) (ties to even) as a residue in [0, m);
@@ -279,6 +291,11 @@ int sda_varint_decode_dev(sda_ctx *ctx, const uint8_t *d_buf, size_t len, int64_
 int sda_fixed_encode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, const float *d_x, size_t n, int64_t *d_out);
 int sda_fixed_decode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, uint64_t divisor, const int64_t *d_in, size_t n,
                          float *d_out);
+/* sda_fixed_encode_dev followed by sda_mask_dev (participate.rs:53-54 on a real-valued update) in ONE pass over the
+ * vector: reads 4 B, writes 8 B per element, the fixed-point vector never exists in memory.  Same results as the two
+ * calls; `modulus` is the encoding modulus and must equal the masking scheme's (None has none of its own). */
+int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t modulus, int frac_bits, const float *d_x,
+                              size_t dim, const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out);
 
 /* Synthetic benchmark / test inputs, generated on the device: out[i] = value(start + i) where
  * value(e) = u64 draw e of ChaCha20(key "sda-b200-synthetic-v1", key word 7 = stream) mod m.

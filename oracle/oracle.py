@@ -274,3 +274,14 @@ def synth_fill(stream, modulus, start, count):
 
 def find_root_of_order(p, q):
     return lib().sdao_find_root_of_order(p, q)
+
+
+def snapshot_transpose(blobs):
+    """server/src/stores.rs:86-101 `iter_snapshot_clerk_jobs_data`: blobs[p][c] (bytes) of P participations x n clerks ->
+    one list per clerk holding that clerk's blob of every participation, in participation order (`shares[ix].push(share.1)`)."""
+    n = len(blobs[0]) if blobs else 0
+    shares = [[] for _ in range(n)]
+    for participation in blobs:
+        for ix, share in enumerate(participation):
+            shares[ix].append(share)
+    return shares

@@ -397,6 +397,20 @@ class Context:
     def fixed_encode_dev(self, modulus, frac_bits, d_x, n, d_out):
         self.check(self._lib.sda_fixed_encode_dev(self._h, modulus, frac_bits, _dev_ptr(d_x), n, _dev_ptr(d_out)))
 
+    def snapshot_transpose_dev(self, d_blobs, offsets, P, n, d_out):
+        """server/src/snapshot.rs:11-27: blob (p, c) -> clerk-major; returns the clerk-major offsets (numpy u64, P n + 1)"""
+        off = np.ascontiguousarray(np.asarray(offsets, dtype=np.uint64))
+        if off.size != P * n + 1:
+            raise ValueError("offsets must have P * n + 1 entries")
+        out_off = np.zeros(P * n + 1, dtype=np.uint64)
+        self.check(self._lib.sda_snapshot_transpose_dev(self._h, _dev_ptr(d_blobs), _ptr(off), P, n, _dev_ptr(d_out), _ptr(out_off)))
+        return out_off
+
+    def fixed_encode_mask_dev(self, scheme, modulus, frac_bits, d_x, dim, rng_seed, d_mask_out, d_masked_out):
+        """fixed_encode_dev + mask_dev in one pass (float32 in, masked residues out)"""
+        self.check(self._lib.sda_fixed_encode_mask_dev(self._h, C.byref(scheme.c), modulus, frac_bits, _dev_ptr(d_x), dim,
+                                                       _seed(rng_seed), _dev_ptr(d_mask_out), _dev_ptr(d_masked_out)))
+
     def fixed_decode_dev(self, modulus, frac_bits, divisor, d_in, n, d_out):
         self.check(self._lib.sda_fixed_decode_dev(self._h, modulus, frac_bits, divisor, _dev_ptr(d_in), n, _dev_ptr(d_out)))
 

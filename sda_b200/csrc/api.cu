@@ -703,10 +703,16 @@ int mask_validate(sda_ctx *ctx, const sda_masking_scheme *s) {
 // Full: mask = dim draws of rng(seed); ChaCha: seed words = first words of rng(seed), mask stream
 // = ChaCha20(seed words).  d_mask_out: Full -> [dim]; ChaCha -> unused (seed words returned in
 // seed_words_out by the caller).
+// d_x != nullptr: the secrets are the fixed-point encodings (frac_bits) of the real vector d_x, produced in the same pass
 int mask_core(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secrets, size_t dim,
-              const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *seed_words_out, int64_t *d_masked_out) {
+              const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *seed_words_out, int64_t *d_masked_out,
+              const float *d_x = nullptr, int frac_bits = 0, int64_t encode_modulus = 0) {
     OK(mask_validate(ctx, s));
     if (s->kind == SDA_MASK_NONE) {   // none.rs:14-18
+        if (d_x) {
+            if (dim) CU(launch_fixed_encode(ctx->lc(), make_field((uint64_t)encode_modulus), frac_bits, d_x, dim, d_masked_out));
+            return SDA_OK;
+        }
         if (dim && d_masked_out != d_secrets)
             CU(cudaMemcpyAsync(d_masked_out, d_secrets, dim * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
         return SDA_OK;
@@ -735,10 +741,14 @@ int mask_core(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secret
     }
     if (dim == 0) return SDA_OK;
     OK(clear_flags(ctx));
-    CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, nullptr, mask_dst, d_masked_out, ctx->d_flag));
+    CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, nullptr, mask_dst, d_masked_out, ctx->d_flag, d_x, frac_bits));
     unsigned rejected = 0;
     OK(read_flags(ctx, &rejected, nullptr));
     if (!rejected) return SDA_OK;
+    if (d_x) {   // the exact path reads i64 secrets: encode first, then mask in place
+        CU(launch_fixed_encode(ctx->lc(), f, frac_bits, d_x, dim, d_masked_out));
+        d_secrets = d_masked_out;
+    }
     CU(ctx->draws.reserve(dim * sizeof(uint64_t)));
     OK(draw_exact(ctx, dr, rounds, key, dim, (uint64_t *)ctx->draws.p));
     CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, (const uint64_t *)ctx->draws.p, mask_dst,
@@ -1185,6 +1195,27 @@ int sda_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_sec
     return mask_core(ctx, s, d_secrets, dim, rng_seed, d_mask_out, nullptr, d_masked_out);
 }
 
+int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t modulus, int frac_bits, const float *d_x,
+                              size_t dim, const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
+    if (frac_bits < 0 || frac_bits > 52) return fail(ctx, SDA_ERR_INVALID, "frac_bits must be in [0, 52]");
+    if (s && s->kind != SDA_MASK_NONE && s->modulus != modulus)
+        return fail(ctx, SDA_ERR_INVALID, "the masking scheme's modulus differs from the encoding modulus");
+    if (s && s->kind == SDA_MASK_CHACHA) {
+        int64_t words[8] = {0};
+        OK(mask_core(ctx, s, nullptr, dim, rng_seed, nullptr, words, d_masked_out, d_x, frac_bits, modulus));
+        const size_t nw = sda_mask_len(s, dim);
+        if (nw && d_mask_out) {
+            CU(cudaMemcpyAsync(d_mask_out, words, nw * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        return SDA_OK;
+    }
+    return mask_core(ctx, s, nullptr, dim, rng_seed, d_mask_out, nullptr, d_masked_out, d_x, frac_bits, modulus);
+}
+
 int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_masks, size_t P, size_t mask_len,
                          int64_t *d_out) {
     if (!ctx) return SDA_ERR_INVALID;
@@ -1605,6 +1636,34 @@ int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, s
     CU(launch_submod(ctx->lc(), make_field((uint64_t)s->modulus), (const int64_t *)ctx->in.p, (const int64_t *)ctx->aux.p,
                      dim, (int64_t *)ctx->out.p));
     return d2h(ctx, out, ctx->out.p, bytes);
+}
+
+// ---- server snapshot transpose -------------------------------------------------------------------
+int sda_snapshot_transpose_dev(sda_ctx *ctx, const uint8_t *d_blobs, const uint64_t *offsets, size_t P, size_t n,
+                               uint8_t *d_out, uint64_t *out_offsets) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    const size_t blobs = P * n;
+    if (!offsets || !out_offsets) return fail(ctx, SDA_ERR_INVALID, "null offsets");
+    // clerk-major offsets: clerk c's job is blob c of every participation, in participation order (stores.rs:95-99)
+    for (size_t i = 0; i < blobs; i++)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, SDA_ERR_INVALID, "offsets must be non-decreasing");
+    uint64_t at = 0;
+    for (size_t c = 0; c < n; c++)
+        for (size_t p = 0; p < P; p++) {
+            out_offsets[c * P + p] = at;
+            at += offsets[p * n + c + 1] - offsets[p * n + c];
+        }
+    out_offsets[blobs] = at;
+    if (blobs == 0 || at == 0) return SDA_OK;
+    if (!d_blobs || !d_out) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    CU(ctx->scratch.reserve(2 * (blobs + 1) * sizeof(uint64_t)));
+    uint64_t *d_in_off = (uint64_t *)ctx->scratch.p, *d_out_off = d_in_off + blobs + 1;
+    CU(cudaMemcpyAsync(d_in_off, offsets, (blobs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(d_out_off, out_offsets, (blobs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_snapshot_transpose(ctx->lc(), d_blobs, d_in_off, P, n, d_out, d_out_off));
+    CU(cudaStreamSynchronize(ctx->stream));   // the offset arrays are the caller's (pageable) memory
+    return SDA_OK;
 }
 
 // ---- multi-GPU clerk sum (clerk.rs:85-86 when one box holds several GPUs) ------------------------------

@@ -55,7 +55,9 @@ cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, con
 // participant side of the ChaCha mask (chacha.rs:36-45)
 cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
                         const int64_t *secrets, size_t dim, const ChaChaKey &key, const uint64_t *draws,
-                        int64_t *mask_out, int64_t *masked_out, unsigned *flag);
+                        int64_t *mask_out, int64_t *masked_out, unsigned *flag, const float *fx = nullptr, int frac_bits = 0);
+// fx != nullptr: the secrets are the fixed-point encodings of fx[dim] (sda_fixed_encode_dev's definition), computed in
+// the same pass; `secrets` is ignored
 // ChaCha mask re-expansion (chacha.rs:60-73): out[i] = sum_p draw_p(i) mod m over P keys
 cudaError_t launch_chacha_mask_combine(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr,
                                        const ChaChaKey *keys, size_t P, size_t dim, int64_t *out,
@@ -150,6 +152,11 @@ cudaError_t launch_fixed_encode(const LaunchCtx &lc, const FieldParams &f, int f
                                 int64_t *out);
 cudaError_t launch_fixed_decode(const LaunchCtx &lc, const FieldParams &f, int frac_bits, uint64_t divisor,
                                 const int64_t *in, size_t n, float *out);
+
+// ---- server snapshot transpose (snapshot.cu; server/src/snapshot.rs:11-27, stores.rs:86-101) ---------------------
+// blob (p, c) of `in` (bytes [in_off[p n + c], in_off[p n + c + 1])) -> `out` at out_off[c P + p]; offsets are device arrays
+cudaError_t launch_snapshot_transpose(const LaunchCtx &lc, const uint8_t *in, const uint64_t *d_in_off, size_t P, size_t n,
+                                      uint8_t *out, const uint64_t *d_out_off);
 
 // ---- synthetic inputs ---------------------------------------------------------------------
 cudaError_t launch_synth_fill(const LaunchCtx &lc, const FieldParams &f, uint32_t stream_id, uint64_t start,

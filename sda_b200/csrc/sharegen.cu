@@ -179,18 +179,35 @@ additive_split_mem_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t
 // ------------------------------------------------------------------------------------------
 // masks: one draw per element
 // ------------------------------------------------------------------------------------------
-template <bool M61, uint32_t DK, int ROUNDS, bool FROM_MEM>
+// FLOAT_IN: the secrets are real values; they are brought to fixed point here (q = rint(x 2^frac_bits) as a canonical
+// residue, the definition of sda_fixed_encode_dev) instead of being read as i64 -- the fused encode + mask of a model
+// update (4 B in, 8 B out per element, no intermediate i64 vector).
+template <bool M61, uint32_t DK, int ROUNDS, bool FROM_MEM, bool FLOAT_IN = false>
 __global__ void __launch_bounds__(CTA)
 mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, const uint64_t *__restrict__ draws,
             int64_t *__restrict__ mask_out, int64_t *__restrict__ masked_out, FieldParams f, DrawParams dr,
-            int lanes, unsigned *flag) {
+            int lanes, unsigned *flag, const float *__restrict__ fx = nullptr, double scale = 1.0) {
     constexpr int G = 8;
     const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
     const size_t e0 = u * G;
     if (e0 >= dim) return;
     const int nvalid = (int)min((size_t)G, dim - e0);
     int64_t x[G], mk[G], md[G];
-    load_run<G>(secrets + e0, x, nvalid, lanes);
+    if constexpr (FLOAT_IN) {
+        float v[G];
+        if (nvalid == G && (reinterpret_cast<uintptr_t>(fx + e0) & 15) == 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(fx + e0)), b = __ldg(reinterpret_cast<const float4 *>(fx + e0) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < G; e++) v[e] = e < nvalid ? __ldg(fx + e0 + e) : 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < G; e++) x[e] = (int64_t)canon<M61>(f, __double2ll_rn((double)v[e] * scale));
+    } else {
+        load_run<G>(secrets + e0, x, nvalid, lanes);
+    }
     uint64_t blk[8];
     bool rej = false;
     if (FROM_MEM) {
@@ -537,10 +554,29 @@ cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, con
 
 cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
                         const int64_t *secrets, size_t dim, const ChaChaKey &key, const uint64_t *draws,
-                        int64_t *mask_out, int64_t *masked_out, unsigned *flag) {
+                        int64_t *mask_out, int64_t *masked_out, unsigned *flag, const float *fx, int frac_bits) {
     if (dim == 0) return cudaSuccess;
     const size_t units = (dim + 7) / 8;
     const unsigned grid = (unsigned)((units + CTA - 1) / CTA);
+    if (fx != nullptr) {                     // fused fixed-point encode + mask, in-kernel draws only
+        if (draws != nullptr) return cudaErrorInvalidValue;
+        const double scale = ldexp(1.0, frac_bits);
+        int fl = pick_lanes(masked_out, 4, 8);
+        if (mask_out && pick_lanes(mask_out, 4, 8) < fl) fl = pick_lanes(mask_out, 4, 8);
+#define SDA_MF(M61, DK, R) mask_kernel<M61, DK, R, false, true><<<grid, CTA, 0, lc.stream>>>(nullptr, dim, key, nullptr, mask_out, masked_out, f, dr, fl, flag, fx, scale)
+        if (f.kind == FIELD_MERSENNE61) {
+            if (rounds == 8) SDA_MF(true, DRAW_M61, 8);
+            else if (rounds == 12) SDA_MF(true, DRAW_M61, 12);
+            else SDA_MF(true, DRAW_M61, 20);
+        } else {
+            if (rounds == 8) SDA_MF(false, DRAW_GENERIC, 8);
+            else if (rounds == 12) SDA_MF(false, DRAW_GENERIC, 12);
+            else SDA_MF(false, DRAW_GENERIC, 20);
+        }
+#undef SDA_MF
+        ++*lc.nlaunch;
+        return cudaGetLastError();
+    }
     int lanes = pick_lanes(secrets, 4, 8);
     const int l2 = pick_lanes(masked_out, 4, 8), l3 = mask_out ? pick_lanes(mask_out, 4, 8) : 4;
     if (l2 < lanes) lanes = l2;

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import sda_b200
+import util
 from sda_b200 import SdaClientError, params
 
 pytestmark = pytest.mark.gpu
@@ -92,3 +93,49 @@ def test_varint_decode_rejects_malformed_streams(ctx):
 def torch_cuda():
     import torch
     return torch
+
+
+# ---- server snapshot transpose: server/src/snapshot.rs:11-27, stores.rs:86-101 ------------------
+@pytest.mark.parametrize("P,n,maxlen", [(1, 1, 5), (3, 2, 0), (7, 3, 40), (64, 9, 3000), (1000, 5, 17), (2, 8, 100_000)])
+def test_snapshot_transpose_matches_the_reference_regrouping(ctx, oracle, P, n, maxlen):
+    """variable-length blobs (empty ones included), every alignment: clerk-major bytes and offsets against the oracle"""
+    import torch as t
+    rng = np.random.default_rng(P * 131 + n)
+    blobs = [[rng.integers(0, 256, size=int(rng.integers(0, maxlen + 1)), dtype=np.uint8).tobytes() for _ in range(n)]
+             for _ in range(P)]
+    flat = b"".join(b for part in blobs for b in part)
+    offsets = np.cumsum([0] + [len(b) for part in blobs for b in part]).astype(np.uint64)
+    d_in = t.from_numpy(np.frombuffer(flat + b"\0", dtype=np.uint8).copy()).cuda()
+    d_out = t.zeros(len(flat) + 1, dtype=t.uint8, device="cuda")
+    out_off = ctx.snapshot_transpose_dev(d_in, offsets, P, n, d_out)
+    ctx.synchronize()
+    got = d_out.cpu().numpy().tobytes()
+    expect = oracle.snapshot_transpose(blobs)
+    assert got[:len(flat)] == b"".join(b for job in expect for b in job)
+    for c in range(n):
+        for p in range(P):
+            assert got[int(out_off[c * P + p]):int(out_off[c * P + p + 1])] == blobs[p][c]
+    assert int(out_off[-1]) == len(flat)
+
+
+def test_snapshot_transpose_of_varint_coded_shares_feeds_the_clerk(ctx, oracle):
+    """participant shares -> varint wire coding per clerk -> snapshot transpose -> the clerk decodes its job and sums"""
+    import torch as t
+    from sda_b200 import params
+    s = params.config3()
+    P, dim = 5, 3001
+    n, B = s.output_size(), s.batches(dim)
+    rng = np.random.default_rng(3)
+    shares = [ctx.share_generate(s, rng.integers(0, s.modulus, size=dim, dtype=np.int64), util.seed_bytes(f"snap/{p}"))
+              for p in range(P)]
+    blobs = [[ctx.varint_encode(shares[p][c]) for c in range(n)] for p in range(P)]
+    flat = b"".join(b for part in blobs for b in part)
+    offsets = np.cumsum([0] + [len(b) for part in blobs for b in part]).astype(np.uint64)
+    d_out = t.zeros(len(flat), dtype=t.uint8, device="cuda")
+    out_off = ctx.snapshot_transpose_dev(t.from_numpy(np.frombuffer(flat, dtype=np.uint8).copy()).cuda(), offsets, P, n, d_out)
+    job = d_out.cpu().numpy().tobytes()
+    for c in range(n):
+        rows = [ctx.varint_decode(job[int(out_off[c * P + p]):int(out_off[c * P + p + 1])]) for p in range(P)]
+        assert all(len(r) == B for r in rows)
+        assert np.array_equal(ctx.share_combine(s, np.stack(rows)),
+                              oracle.canonical(s.modulus, oracle.share_combine(s.modulus, np.stack([shares[p][c] for p in range(P)]))))

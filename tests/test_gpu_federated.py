@@ -102,3 +102,38 @@ def test_federated_round_trip(ctx, oracle):
     mean = d_mean.cpu().numpy()
     assert np.array_equal(mean, oracle.fixed_decode(summed, FRAC, P61, P))
     assert np.max(np.abs(mean - updates.astype(np.float64).mean(axis=0))) < 2.0 ** -24
+
+
+@pytest.mark.parametrize("modulus", [P61, params.P61_GENERIC, 433])
+def test_fused_encode_mask_equals_encode_then_mask(ctx, oracle, modulus):
+    """sda_fixed_encode_mask_dev == sda_fixed_encode_dev + sda_mask_dev, and both == the oracle, for every mask scheme"""
+    import torch as t
+    rng = np.random.default_rng(31)
+    for dim in (1, 7, 8, 9, 1000, 40003):
+        x = (rng.standard_normal(dim) * 3).astype(np.float32)
+        q = oracle.fixed_encode(x, FRAC, modulus)
+        d_x = t.from_numpy(x).cuda()
+        for ms in (LMS.None_(), LMS.Full(modulus), LMS.ChaCha(modulus, dim, 128), LMS.ChaCha(modulus, dim, 40)):
+            seed = util.seed_bytes(f"fusedmask/{dim}/{modulus}")
+            nmask = ms.mask_len(dim)
+            d_mask = t.zeros(max(nmask, 1), dtype=t.int64, device="cuda")
+            d_masked = t.empty(dim, dtype=t.int64, device="cuda")
+            ctx.fixed_encode_mask_dev(ms, modulus, FRAC, d_x[1:] if False else d_x, dim, seed, d_mask, d_masked)
+            ctx.synchronize()
+            emask, emasked = oracle.mask(util.to_oracle_masking(oracle, ms), q, oracle.rng_from_seed_bytes(seed))
+            assert np.array_equal(d_masked.cpu().numpy(), util.canon(oracle, modulus, emasked)), (dim, modulus, ms)
+            assert d_mask.cpu().numpy()[:nmask].tolist() == util.canon(oracle, modulus, emask).tolist() if nmask and ms.c.kind == 1 \
+                else d_mask.cpu().numpy()[:nmask].tolist() == list(emask)
+    # an unaligned float vector takes the scalar loads
+    x = rng.standard_normal(1001).astype(np.float32)
+    d_x = t.from_numpy(x).cuda()
+    d_masked = t.empty(1000, dtype=t.int64, device="cuda")
+    d_mask = t.zeros(1000, dtype=t.int64, device="cuda")
+    ms = LMS.Full(P61)
+    seed = util.seed_bytes("fusedmask/unaligned")
+    ctx.fixed_encode_mask_dev(ms, P61, FRAC, d_x[1:], 1000, seed, d_mask, d_masked)
+    ctx.synchronize()
+    _, emasked = oracle.mask(util.to_oracle_masking(oracle, ms), oracle.fixed_encode(x[1:], FRAC, P61), oracle.rng_from_seed_bytes(seed))
+    assert np.array_equal(d_masked.cpu().numpy(), util.canon(oracle, P61, emasked))
+    with pytest.raises(sda_b200.SdaClientError, match="differs"):
+        ctx.fixed_encode_mask_dev(LMS.Full(433), P61, FRAC, d_x, 10, seed, d_mask, d_masked)

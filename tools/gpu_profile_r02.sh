@@ -1,0 +1,28 @@
+#!/bin/bash
+# round-2 evidence run on one B200: launch list of a bench step, full ncu captures of the dominant kernels at the bench
+# configuration, and the clocks during a 20-step bench (the driver's command line)
+mkdir -p gpurun_out
+Q="--no-e2e --no-cpu-baseline --no-round-sweep --no-configs45"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/r02_launches.csv \
+    python bench.py --steps 2 --warmup 3 $Q > gpurun_out/r02_ncu_launches.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:packed_share_tc2 -s 3 -c 1 -o gpurun_out/r02_k2 \
+    python bench.py --steps 1 --warmup 3 $Q > gpurun_out/r02_ncu_k2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:combine_kernel -s 30 -c 1 -o gpurun_out/r02_k3 \
+    python bench.py --steps 1 --warmup 3 $Q > gpurun_out/r02_ncu_k3.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:packed_share_tcg -c 1 -o gpurun_out/r02_tcg \
+    python - > gpurun_out/r02_ncu_tcg.log 2>&1 <<'PY'
+import hashlib, torch, sda_b200
+from sda_b200 import params
+ctx = sda_b200.Context(0)
+s = params.LinearSecretSharingScheme.PackedShamir(3, 7, 3, params.P61, params.ROOT_ORDER_31, params.ROOT_ORDER_41)
+P, dim = 64, 10_000_000
+sec = torch.empty((P, dim), dtype=torch.int64, device="cuda"); ctx.synth_fill_dev(3, params.P61, 0, P * dim, sec)
+out = torch.empty((P, 7, s.batches(dim)), dtype=torch.int64, device="cuda")
+seeds = b"".join(hashlib.sha256(b"%d" % i).digest() for i in range(P))
+ctx.share_generate_dev(s, sec, dim, P, dim, seeds, out); ctx.synchronize()
+PY
+timeout 600 python bench.py --steps 20 --warmup 5 --no-configs45 > gpurun_out/r02_bench_20.json 2> gpurun_out/r02_bench_20.err
+python -c "
+import json; d=json.load(open('gpurun_out/r02_bench_20.json')); print('20 steps: frac %.4f ms %.3f value %.4g e2e %.4g' % (d['roofline']['frac'], d['roofline']['ms_per_launch'], d['value'], d['e2e']['value']), d['clocks'])"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit,memory.total --format=csv > gpurun_out/r02_smi.txt 2>&1
+lscpu | head -20 > gpurun_out/r02_lscpu.txt 2>&1
