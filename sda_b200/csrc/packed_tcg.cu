@@ -11,9 +11,11 @@
 // Row layout (K-major, no swizzle, tc_common.cuh): chunk c of a row is 16 bytes = two u64 values; chunks
 // 0 .. DC-1 hold the t draws (DC = ceil(t/2)), chunks DC .. DC+SC-1 the k secrets (SC = ceil(k/2)); a half chunk
 // without a value and the chunk that pads an odd chunk count to whole 32-byte K steps meet zero rows of B.
-// A pass of a CTA = G tiles of 128 consecutive batches of one participant (G = 2, or 1 for n > 16): all G tiles are
-// multiplied at once into G accumulators, then every thread folds the limb sums of its row, one share at a time
-// (tcgen05.ld x8 per share), and stores them; consecutive threads own consecutive batches, so stores coalesce.
+// A pass of a CTA = GS tiles of 128 consecutive batches of one participant (GS = 2 .. 8, chosen so that the pass's
+// 16 GS t keystream blocks fill the 128 threads): the tiles are multiplied G at a time into G accumulators (G = 2, or 1
+// for n > 16), and after each round every thread folds the limb sums of its rows, one share at a time (tcgen05.ld x8 per
+// share, the next load issued under the current fold), and stores them; consecutive threads own consecutive batches, so
+// stores coalesce.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -32,11 +34,11 @@ constexpr int CTAG = 128;
 struct GShape {
     int k, t, n;
     int dc, sc, nch, nk;          // chunks of draws / secrets / per row, K steps
-    int nmma, acc_cols, g;        // MMA N, TMEM columns per accumulator, tiles per pass
+    int nmma, acc_cols, g, gs;    // MMA N, TMEM columns per accumulator, accumulators (tiles multiplied at once), tiles staged per pass
     int w5;                       // limb plan of the Mersenne path (packed_tc2.cu); 8 = plain bytes
     uint32_t sbo_a, a_tile, a_bytes, sbo_b, b_bytes;
     uint32_t idesc;
-    uint32_t blocks_per_pass;     // keystream blocks a pass consumes: 16 g t
+    uint32_t blocks_per_pass;     // keystream blocks a pass consumes: 16 gs t
 };
 
 inline int w5_for_g(int kt) {
@@ -58,11 +60,26 @@ GShape make_shape(int k, int t, int n, bool m61) {
     s.w5 = m61 ? w5_for_g(k + t) : 8;
     s.sbo_a = (uint32_t)s.nch * 128;
     s.a_tile = 16 * s.sbo_a;
-    s.a_bytes = (uint32_t)s.g * s.a_tile + 128;      // an odd chunk count reads one chunk past the last row group
+    // tiles staged per pass: a pass consumes 16 gs t keystream blocks, one per thread and round; the more of the 128
+    // threads have a block in the last round the better (t = 2 needs gs = 4, t = 1 gs = 8), within 64 KB of operand tiles
+    s.gs = s.g;
+    {
+        double best = 0;
+        for (int gs = s.g; gs <= 8; gs *= 2) {
+            if ((size_t)gs * s.a_tile > 64 * 1024 && gs > s.g) break;
+            const int blocks = 16 * gs * t, rounds = (blocks + CTAG - 1) / CTAG;
+            const double eff = (double)blocks / (rounds * CTAG);
+            if (eff > best + 1e-9) {
+                best = eff;
+                s.gs = gs;
+            }
+        }
+    }
+    s.a_bytes = (uint32_t)s.gs * s.a_tile + 128;     // an odd chunk count reads one chunk past the last row group
     s.sbo_b = 2 * (uint32_t)s.nk * 128;
     s.b_bytes = (uint32_t)(s.nmma / 8) * s.sbo_b;
     s.idesc = idesc_u8(s.nmma);
-    s.blocks_per_pass = 16u * (uint32_t)s.g * (uint32_t)t;
+    s.blocks_per_pass = 16u * (uint32_t)s.gs * (uint32_t)t;
     return s;
 }
 
@@ -171,8 +188,8 @@ packed_share_tcg_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
     const uint32_t full_bar = smem_u32(&mbar), a_base = smem_u32(sA), b_base = smem_u32(sB);
     uint32_t parity = 0;
 
-    const uint32_t K = (uint32_t)S.k, T = (uint32_t)S.t, N = (uint32_t)S.n, G = (uint32_t)S.g;
-    const uint32_t pass_batches = G * CTAG;
+    const uint32_t K = (uint32_t)S.k, T = (uint32_t)S.t, N = (uint32_t)S.n, G = (uint32_t)S.g, GS = (uint32_t)S.gs;
+    const uint32_t pass_batches = GS * CTAG;
     const uint32_t sh3 = 8u + (uint32_t)S.w5, nbits = 21u - (uint32_t)S.w5, mask3 = LOW29 & ~((1u << sh3) - 1u);
     const uint32_t step_p = gridDim.x / units_per_p, step_u = gridDim.x % units_per_p;
     const uint32_t unit_end = unit_begin + units_per_p;
@@ -183,7 +200,7 @@ packed_share_tcg_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         // ---- secrets of row `tid` of every tile: canonical, zero beyond the vector (batched.rs:38-43) ------------
         {
             const int64_t *sec = secrets + (size_t)p * ld;
-            for (uint32_t q = 0; q < G; q++) {
+            for (uint32_t q = 0; q < GS; q++) {
                 const size_t e0 = (b0 + q * CTAG + tid) * K;
                 uint8_t *row = sA + q * S.a_tile + (tid >> 3) * S.sbo_a + (tid & 7) * 16 + (uint32_t)S.dc * LBO;
                 for (uint32_t i = 0; i < K; i++) {
@@ -231,38 +248,49 @@ packed_share_tcg_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                 if (bad) atomicOr(flag, 1u);
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (warp == 0) {
-            uint32_t elected;
-            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
-            if (elected) {
-                const uint64_t db = umma_desc(b_base, S.sbo_b);
-                for (uint32_t q = 0; q < G; q++) {
-                    const uint64_t da = umma_desc(a_base + q * S.a_tile, S.sbo_a);
-                    for (uint32_t kk = 0; kk < (uint32_t)S.nk; kk++)
-                        umma_i8(taddr + q * (uint32_t)S.acc_cols, da + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S.idesc, kk > 0);
+        // ---- rounds of G tiles: multiply into the G accumulators, then every thread folds and stores its rows -----------
+        for (uint32_t q0 = 0; q0 < GS; q0 += G) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();          // operand rows complete (first round) / accumulators read out (later rounds)
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (warp == 0) {
+                uint32_t elected;
+                asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(elected));
+                if (elected) {
+                    const uint64_t db = umma_desc(b_base, S.sbo_b);
+                    for (uint32_t q = 0; q < G; q++) {
+                        const uint64_t da = umma_desc(a_base + (q0 + q) * S.a_tile, S.sbo_a);
+                        for (uint32_t kk = 0; kk < (uint32_t)S.nk; kk++)
+                            umma_i8(taddr + q * (uint32_t)S.acc_cols, da + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S.idesc, kk > 0);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(full_bar) : "memory");
+                __syncwarp();
             }
-            __syncwarp();
-        }
-        mbar_wait(full_bar, parity);
-        parity ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- fold and store: share j of batch b at out[p][j][b] --------------------------------------------------
-        for (uint32_t q = 0; q < G; q++) {
-            const size_t b = b0 + q * CTAG + tid;
-            int64_t *o = out + (size_t)p * N * B + b;
-            const bool live = b < B;
-            for (uint32_t j = 0; j < N; j++) {
-                uint32_t d[8];
-                tmem_ld8(my_taddr + q * (uint32_t)S.acc_cols + 8 * j, d);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                const uint64_t r = compose_g<M61>(d, sh3, nbits, mask3, gp.f);
-                if (live) o[(size_t)j * B] = (int64_t)r;
+            mbar_wait(full_bar, parity);
+            parity ^= 1;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // share j of batch b at out[p][j][b]; the TMEM load of the next share runs under the fold of the current one
+            for (uint32_t q = 0; q < G; q++) {
+                const size_t b = b0 + (q0 + q) * CTAG + tid;
+                int64_t *o = out + (size_t)p * N * B + b;
+                const bool live = b < B;
+                const uint32_t tq = my_taddr + q * (uint32_t)S.acc_cols;
+                uint32_t d0[8], d1[8];
+                tmem_ld8(tq, d0);
+                for (uint32_t j = 0; j < N; j += 2) {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (j + 1 < N) tmem_ld8(tq + 8 * (j + 1), d1);
+                    const uint64_t r0 = compose_g<M61>(d0, sh3, nbits, mask3, gp.f);
+                    if (live) o[(size_t)j * B] = (int64_t)r0;
+                    if (j + 1 < N) {
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (j + 2 < N) tmem_ld8(tq + 8 * (j + 2), d0);
+                        const uint64_t r1 = compose_g<M61>(d1, sh3, nbits, mask3, gp.f);
+                        if (live) o[(size_t)(j + 1) * B] = (int64_t)r1;
+                    }
+                }
             }
         }
         // every thread has read its lanes before it reaches the next pass's barrier, after which TMEM is overwritten
@@ -290,7 +318,7 @@ cudaError_t launch_g(const LaunchCtx &lc, const GParams &gp, const int64_t *secr
                      size_t first_batch, size_t n_batches, const ChaChaKey *keys, const uint8_t *d_b_image, int64_t *out,
                      unsigned *flag) {
     const GShape &S = gp.s;
-    const size_t pass = (size_t)S.g * CTAG;
+    const size_t pass = (size_t)S.gs * CTAG;
     const size_t B = (dim + S.k - 1) / S.k;
     if (first_batch % pass != 0 || first_batch > B) return cudaErrorInvalidValue;
     if (n_batches > B - first_batch) n_batches = B - first_batch;
@@ -322,7 +350,7 @@ bool packed_share_tcg_supported(int k, int t, int n) { return k >= 1 && t >= 1 &
 
 size_t packed_share_tcg_image_bytes(int k, int t, int n) { return make_shape(k, t, n, true).b_bytes; }
 
-size_t packed_share_tcg_slice_batches(int k, int t, int n) { return (size_t)make_shape(k, t, n, true).g * CTAG; }
+size_t packed_share_tcg_slice_batches(int k, int t, int n) { return (size_t)make_shape(k, t, n, true).gs * CTAG; }
 
 // the constant operand as it lies in shared memory (limb plan of the Mersenne path when p = 2^61 - 1, plain bytes otherwise)
 void packed_share_tcg_build_image(int k, int t, int n, const Matrix &m, uint64_t p, uint8_t *img) {

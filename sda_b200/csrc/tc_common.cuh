@@ -85,15 +85,17 @@ __device__ __forceinline__ void umma_i8(uint32_t taddr, uint64_t da, uint64_t db
 }
 // the retry loop lives inside the asm block: written as a C loop around try_wait, ptxas recomputes the
 // barrier's shared-window address (S2R SR_CgaCtaId, MOV, LEA) on every iteration of the spin
+// try_wait suspends the thread for up to the time hint (ns) before it reports failure: with a generous hint a waiting warp
+// sleeps instead of re-issuing the test (profiles/r02_k2.md: the retries were 1.2 % of the share-gen kernel's instructions)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n"
         "SDA_MBAR_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra SDA_MBAR_DONE;\n\t"
         "bra SDA_MBAR_WAIT;\n"
         "SDA_MBAR_DONE:\n\t}"
-        :: "r"(bar), "r"(parity) : "memory");
+        :: "r"(bar), "r"(parity), "r"(1000000u) : "memory");
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
