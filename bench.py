@@ -361,6 +361,14 @@ def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
         d_mask = torch.empty(dim, dtype=torch.int64, device="cuda")
         timed("mask_expand", lambda: ctx.mask_combine_dev(ms_, d_seedw, P, words, d_mask))
 
+        if world > 1:            # NCCL sets up its channels for a payload size on first use: keep that out of the timed exchange
+            warm = torch.zeros(max(n * B, dim), dtype=torch.int64, device="cuda")
+            ctx.partial_sums_reduce_dev(p, warm, n * B, 0)
+            ctx.partial_sums_reduce_dev(p, warm, dim, 0)
+            ctx.synchronize()
+            del warm
+            dist.barrier()
+
         def reduce_all():
             ctx.partial_sums_reduce_dev(p, d_sum, n * B, 0)
             ctx.partial_sums_reduce_dev(p, d_mask, dim, 0)
