@@ -351,8 +351,8 @@ def run_config5(ctx, stream, torch, dist, world, rank, participants, tile):
             stream.synchronize()
 
             def encode_mask():     # one pass per participant: float -> fixed point -> + ChaCha mask (participate.rs:53-54)
-                for i in range(pt):
-                    ctx.fixed_encode_mask_dev(ms_, p, FRAC, d_x[i], dim, sd(f"fed/mask/{rank}/{t0 + i}"), d_seedw[t0 + i], d_m[i])
+                ctx.fixed_encode_mask_dev(ms_, p, FRAC, d_x, dim, b"".join(sd(f"fed/mask/{rank}/{t0 + i}") for i in range(pt)),
+                                          d_seedw[t0:], d_m, P=pt)
             timed("encode_mask", encode_mask)
             seeds = b"".join(sd(f"fed/share/{rank}/{t0 + i}") for i in range(pt))
             timed("share_gen_clerk_sum",

@@ -292,10 +292,14 @@ int sda_fixed_encode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, const flo
 int sda_fixed_decode_dev(sda_ctx *ctx, int64_t modulus, int frac_bits, uint64_t divisor, const int64_t *d_in, size_t n,
                          float *d_out);
 /* sda_fixed_encode_dev followed by sda_mask_dev (participate.rs:53-54 on a real-valued update) in ONE pass over the
- * vector: reads 4 B, writes 8 B per element, the fixed-point vector never exists in memory.  Same results as the two
- * calls; `modulus` is the encoding modulus and must equal the masking scheme's (None has none of its own). */
+ * vector, for P participants per call: d_x[P][x_ld] float32 in, d_masked_out[P][masked_ld] residues out, seeds[P][32]
+ * (HOST), d_mask_out[P][mask_len] (Full: the masks; ChaCha: the seed words; may be NULL).  Reads 4 B, writes 8 B per
+ * element, the fixed-point vector never exists in memory; the P kernels are queued back to back with one read-back at the
+ * end.  Same results as the two calls per participant; `modulus` is the encoding modulus and must equal the masking
+ * scheme's (None has none of its own). */
 int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t modulus, int frac_bits, const float *d_x,
-                              size_t dim, const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out);
+                              size_t x_ld, size_t P, size_t dim, const uint8_t *seeds, int64_t *d_mask_out,
+                              int64_t *d_masked_out, size_t masked_ld);
 
 /* Synthetic benchmark / test inputs, generated on the device: out[i] = value(start + i) where
  * value(e) = u64 draw e of ChaCha20(key "sda-b200-synthetic-v1", key word 7 = stream) mod m.

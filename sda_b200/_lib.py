@@ -92,7 +92,7 @@ PROTOTYPES = {
     "sda_snapshot_transpose_dev": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
     "sda_fixed_encode_dev": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
     "sda_fixed_decode_dev": (_int, [_vp, _i64, _int, _u64, _vp, _sz, _vp]),
-    "sda_fixed_encode_mask_dev": (_int, [_vp, _ms, _i64, _int, _vp, _sz, _vp, _vp, _vp]),
+    "sda_fixed_encode_mask_dev": (_int, [_vp, _ms, _i64, _int, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _sz]),
     "sda_synth_fill_dev": (_int, [_vp, C.c_uint32, _i64, _u64, _sz, _vp]),
 }
 

@@ -406,10 +406,17 @@ class Context:
         self.check(self._lib.sda_snapshot_transpose_dev(self._h, _dev_ptr(d_blobs), _ptr(off), P, n, _dev_ptr(d_out), _ptr(out_off)))
         return out_off
 
-    def fixed_encode_mask_dev(self, scheme, modulus, frac_bits, d_x, dim, rng_seed, d_mask_out, d_masked_out):
-        """fixed_encode_dev + mask_dev in one pass (float32 in, masked residues out)"""
-        self.check(self._lib.sda_fixed_encode_mask_dev(self._h, C.byref(scheme.c), modulus, frac_bits, _dev_ptr(d_x), dim,
-                                                       _seed(rng_seed), _dev_ptr(d_mask_out), _dev_ptr(d_masked_out)))
+    def fixed_encode_mask_dev(self, scheme, modulus, frac_bits, d_x, dim, rng_seed, d_mask_out, d_masked_out, P=1, x_ld=None,
+                              masked_ld=None):
+        """fixed_encode_dev + mask_dev in one pass for P participants (float32 rows in, masked residues out); rng_seed is
+        P x 32 bytes"""
+        seeds = bytes(rng_seed)
+        if len(seeds) != 32 * P:
+            raise ValueError("rng_seed must be P x 32 bytes")
+        buf = (C.c_uint8 * len(seeds)).from_buffer_copy(seeds)
+        self.check(self._lib.sda_fixed_encode_mask_dev(self._h, C.byref(scheme.c), modulus, frac_bits, _dev_ptr(d_x),
+                                                       dim if x_ld is None else x_ld, P, dim, buf, _dev_ptr(d_mask_out),
+                                                       _dev_ptr(d_masked_out), dim if masked_ld is None else masked_ld))
 
     def fixed_decode_dev(self, modulus, frac_bits, divisor, d_in, n, d_out):
         self.check(self._lib.sda_fixed_decode_dev(self._h, modulus, frac_bits, divisor, _dev_ptr(d_in), n, _dev_ptr(d_out)))

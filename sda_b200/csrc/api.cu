@@ -1196,24 +1196,63 @@ int sda_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_sec
 }
 
 int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t modulus, int frac_bits, const float *d_x,
-                              size_t dim, const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out) {
+                              size_t x_ld, size_t P, size_t dim, const uint8_t *seeds, int64_t *d_mask_out,
+                              int64_t *d_masked_out, size_t masked_ld) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, s));
     if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
     if (frac_bits < 0 || frac_bits > 52) return fail(ctx, SDA_ERR_INVALID, "frac_bits must be in [0, 52]");
-    if (s && s->kind != SDA_MASK_NONE && s->modulus != modulus)
+    if (s->kind != SDA_MASK_NONE && s->modulus != modulus)
         return fail(ctx, SDA_ERR_INVALID, "the masking scheme's modulus differs from the encoding modulus");
-    if (s && s->kind == SDA_MASK_CHACHA) {
-        int64_t words[8] = {0};
-        OK(mask_core(ctx, s, nullptr, dim, rng_seed, nullptr, words, d_masked_out, d_x, frac_bits, modulus));
-        const size_t nw = sda_mask_len(s, dim);
-        if (nw && d_mask_out) {
-            CU(cudaMemcpyAsync(d_mask_out, words, nw * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-        }
+    if (x_ld < dim || masked_ld < dim) return fail(ctx, SDA_ERR_INVALID, "row stride shorter than the vector");
+    if (P == 0 || dim == 0) return SDA_OK;
+    const size_t nw = sda_mask_len(s, dim);
+    if (s->kind == SDA_MASK_NONE) {
+        for (size_t p = 0; p < P; p++)
+            CU(launch_fixed_encode(ctx->lc(), make_field((uint64_t)modulus), frac_bits, d_x + p * x_ld, dim, d_masked_out + p * masked_ld));
         return SDA_OK;
     }
-    return mask_core(ctx, s, nullptr, dim, rng_seed, d_mask_out, nullptr, d_masked_out, d_x, frac_bits, modulus);
+    if (!seeds) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
+    if (s->kind == SDA_MASK_CHACHA && s->dimension != dim)   // chacha.rs:26
+        return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (chacha.rs:26: scheme dimension %llu, %zu secrets)",
+                    (unsigned long long)s->dimension, dim);
+    // every participant's kernel is queued before anything is read back: one flag read (one stream synchronisation) per
+    // call instead of one per participant
+    const FieldParams f = make_field((uint64_t)s->modulus);
+    const DrawParams dr = make_draw((uint64_t)s->modulus);
+    std::vector<int64_t> words(s->kind == SDA_MASK_CHACHA ? P * nw : 0);
+    OK(clear_flags(ctx));
+    for (size_t p = 0; p < P; p++) {
+        ChaChaKey key = key_from_seed_bytes(seeds + 32 * p);
+        int rounds = ctx->rounds;
+        int64_t *mask_dst = d_mask_out ? d_mask_out + p * nw : nullptr;
+        if (s->kind == SDA_MASK_CHACHA) {
+            uint32_t blk[16], seed[8] = {0};
+            host_chacha_block(key, 0, ctx->rounds, blk);                  // chacha.rs:31-33, OsRng -> injected stream
+            for (size_t i = 0; i < nw; i++) {
+                seed[i] = blk[i];
+                words[p * nw + i] = (int64_t)seed[i];                     // chacha.rs:48-50
+            }
+            key = key_from_words(seed, nw);                               // chacha.rs:36
+            rounds = 20;
+            mask_dst = nullptr;
+        }
+        CU(launch_mask(ctx->lc(), f, dr, rounds, nullptr, dim, key, nullptr, mask_dst, d_masked_out + p * masked_ld, ctx->d_flag,
+                       d_x + p * x_ld, frac_bits));
+    }
+    if (!words.empty() && d_mask_out)
+        CU(cudaMemcpyAsync(d_mask_out, words.data(), words.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned rejected = 0;
+    OK(read_flags(ctx, &rejected, nullptr));        // also: `words` has been copied
+    if (!rejected) return SDA_OK;
+    // a rejected gen_range word somewhere: redo participant by participant on the exact path
+    for (size_t p = 0; p < P; p++) {
+        int64_t w8[8] = {0};
+        OK(mask_core(ctx, s, nullptr, dim, seeds + 32 * p, s->kind == SDA_MASK_CHACHA ? nullptr : (d_mask_out ? d_mask_out + p * nw : nullptr),
+                     s->kind == SDA_MASK_CHACHA ? w8 : nullptr, d_masked_out + p * masked_ld, d_x + p * x_ld, frac_bits, modulus));
+    }
+    return SDA_OK;
 }
 
 int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_masks, size_t P, size_t mask_len,

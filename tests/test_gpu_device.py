@@ -345,3 +345,38 @@ def test_config4_clerk_sum_slice(ctx, oracle, torch_cuda):
     assert host(out[cols]).tolist() == exp.tolist()
     del d_rows
     t.cuda.empty_cache()
+
+
+def test_fused_in_place_redo_does_not_double_count(oracle, torch_cuda, monkeypatch):
+    """sda_share_generate_combine_dev called in place (d_acc_in == d_out) must survive a set gen_range rejection
+    flag: the redo on the materialising path starts from the untouched running sum.  SDA_B200_DEBUG_FORCE_REJECT=1 (read
+    at context creation) makes the library treat the fused kernel's flag as set."""
+    import sda_b200
+    t = torch_cuda
+    s = params.config3()
+    n, dim, P = s.output_size(), 3000, 6
+    B = s.batches(dim)
+    rng = np.random.default_rng(77)
+    secrets = rng.integers(0, s.modulus, size=(2 * P, dim), dtype=np.int64)
+    seeds = b"".join(util.seed_bytes(f"redo/{pi}") for pi in range(2 * P))
+    plain = sda_b200.Context(0)
+    monkeypatch.setenv("SDA_B200_DEBUG_FORCE_REJECT", "1")
+    forced = sda_b200.Context(0)
+    monkeypatch.delenv("SDA_B200_DEBUG_FORCE_REJECT")
+    results = []
+    for c in (plain, forced):
+        d_acc = t.empty((n, B), dtype=t.int64, device="cuda")
+        c.share_generate_combine_dev(s, dev(t, secrets[:P]), dim, P, dim, seeds[:32 * P], d_acc)
+        c.share_generate_combine_dev(s, dev(t, secrets[P:]), dim, P, dim, seeds[32 * P:], d_acc, d_acc_in=d_acc)   # in place
+        c.synchronize()
+        results.append(host(d_acc))
+    assert "draws" not in plain.last_kernel()
+    # expected: per-clerk sums of the oracle's shares of all 2P participants
+    exp = np.zeros((n, B), dtype=object)
+    for pi in range(2 * P):
+        exp += util.canon(oracle, s.modulus, util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)).astype(object)
+    exp = (exp % s.modulus).astype(np.int64)
+    assert np.array_equal(results[0], exp)
+    assert np.array_equal(results[1], exp)
+    plain.close()
+    forced.close()

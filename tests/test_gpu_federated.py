@@ -137,3 +137,18 @@ def test_fused_encode_mask_equals_encode_then_mask(ctx, oracle, modulus):
     assert np.array_equal(d_masked.cpu().numpy(), util.canon(oracle, P61, emasked))
     with pytest.raises(sda_b200.SdaClientError, match="differs"):
         ctx.fixed_encode_mask_dev(LMS.Full(433), P61, FRAC, d_x, 10, seed, d_mask, d_masked)
+    # several participants per call, strided rows: the same as one call per participant
+    P, dim, ld = 5, 777, 800
+    xs = rng.standard_normal((P, ld)).astype(np.float32)
+    seeds = b"".join(util.seed_bytes(f"fusedmask/batch/{pi}") for pi in range(P))
+    for ms in (LMS.Full(P61), LMS.ChaCha(P61, dim, 128)):
+        nm = ms.mask_len(dim)
+        d_masks = t.zeros((P, nm), dtype=t.int64, device="cuda")
+        d_out = t.zeros((P, ld), dtype=t.int64, device="cuda")
+        ctx.fixed_encode_mask_dev(ms, P61, FRAC, t.from_numpy(xs).cuda(), dim, seeds, d_masks, d_out, P=P, x_ld=ld, masked_ld=ld)
+        ctx.synchronize()
+        for pi in range(P):
+            emask, emasked = oracle.mask(util.to_oracle_masking(oracle, ms), oracle.fixed_encode(xs[pi, :dim], FRAC, P61),
+                                         oracle.rng_from_seed_bytes(seeds[32 * pi:32 * pi + 32]))
+            assert np.array_equal(d_out[pi, :dim].cpu().numpy(), util.canon(oracle, P61, emasked))
+            assert d_masks[pi].cpu().numpy().tolist() == [int(v) % P61 for v in emask]
