@@ -496,7 +496,7 @@ int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
 // other primes (or when the context asks for it with SDA_PACKED_PATH_TENSOR_CORES_V1), and the run-time-shaped kernel
 // (packed_tcg.cu) for every other (k, t, n).  All generate batches first_batch .. first_batch + n_batches - 1 of every
 // participant; first_batch is a multiple of share_tc_slice_batches().
-enum { TC_NONE = 0, TC_V1 = 1, TC_PAIRED = 2, TC_RUNTIME = 3 };
+enum { TC_NONE = 0, TC_V1 = 1, TC_PAIRED = 2, TC_RUNTIME = 3, TC_PAIRED_RTN = 4 };
 int tc_kernel_for(const sda_ctx *ctx, const Packed &pk, size_t dim) {
     if (ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES) return TC_NONE;
     if (packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
@@ -504,6 +504,9 @@ int tc_kernel_for(const sda_ctx *ctx, const Packed &pk, size_t dim) {
             return TC_PAIRED;
         return TC_V1;
     }
+    if (pk.p == P61 && ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 &&
+        packed_share_tc2n_supported(pk.k, pk.t, pk.n, dim, ctx->rounds))
+        return TC_PAIRED_RTN;
     return packed_share_tcg_supported(pk.k, pk.t, pk.n) ? TC_RUNTIME : TC_NONE;
 }
 size_t share_tc_slice_batches(const sda_ctx *ctx, const Packed &pk, size_t dim) {
@@ -511,6 +514,7 @@ size_t share_tc_slice_batches(const sda_ctx *ctx, const Packed &pk, size_t dim) 
     case TC_PAIRED: return packed_share_tc2_slice_batches(pk.k, pk.t, pk.n);
     case TC_V1: return packed_share_tc_slice_batches(pk.k, pk.t, pk.n);
     case TC_RUNTIME: return packed_share_tcg_slice_batches(pk.k, pk.t, pk.n);
+    case TC_PAIRED_RTN: return packed_share_tc2n_slice_batches(pk.k, pk.t);
     }
     return 0;
 }
@@ -519,9 +523,12 @@ int ensure_image(sda_ctx *ctx, int which, const Packed &pk, const Matrix &M, Dev
     std::vector<uint64_t> key{(uint64_t)which, (uint64_t)pk.k, (uint64_t)pk.t, (uint64_t)pk.n, pk.p};
     key.insert(key.end(), M.e, M.e + M.rows * M.cols);
     if (key == *cached) return SDA_OK;
-    const size_t ib = which == TC_PAIRED ? packed_share_tc2_image_bytes(pk.k, pk.t, pk.n) : packed_share_tcg_image_bytes(pk.k, pk.t, pk.n);
+    const size_t ib = which == TC_PAIRED ? packed_share_tc2_image_bytes(pk.k, pk.t, pk.n)
+                    : which == TC_PAIRED_RTN ? packed_share_tc2n_image_bytes(pk.k, pk.t)
+                                             : packed_share_tcg_image_bytes(pk.k, pk.t, pk.n);
     std::vector<uint8_t> img(ib);
     if (which == TC_PAIRED) packed_share_tc2_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
+    else if (which == TC_PAIRED_RTN) packed_share_tc2n_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
     else packed_share_tcg_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
     CU(buf->reserve(ib));
     CU(cudaMemcpyAsync(buf->p, img.data(), ib, cudaMemcpyHostToDevice, ctx->stream));
@@ -543,6 +550,12 @@ int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const Field
         CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
         CU(launch_packed_share_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
                                    (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
+        return SDA_OK;
+    case TC_PAIRED_RTN:
+        OK(ensure_image(ctx, TC_PAIRED_RTN, pk, M, &ctx->tc2_image, &ctx->tc2_image_key));
+        CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
+        CU(launch_packed_share_tc2n(ctx->lc(), pk.k, pk.t, pk.n, d_secrets, ld, P, dim, first_batch, n_batches, d_keys,
+                                    (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p, d_out, ctx->d_flag));
         return SDA_OK;
     case TC_RUNTIME:
         OK(ensure_image(ctx, TC_RUNTIME, pk, M, &ctx->tcg_image, &ctx->tcg_image_key));

@@ -1,658 +1,14 @@
-// packed_tc2.cu -- K2 for p = 2^61 - 1, second generation of the byte-limb GEMM of packed_tc.cu
-// (client/src/crypto/sharing/packed_shamir.rs:40-43 -> tss 0.2 `share`, + batched.rs:18-53).
-//
-// The arithmetic is the one packed_tc.cu explains: shares_b = M . [secrets_b ; draws_b] is linear in the BYTES of its
-// inputs, so D = A . B^T with A = the raw bytes of the rows and B = the limbs of (M[j][i] 2^{8c} mod p) is a dense
-// u8 GEMM on tcgen05.mma.kind::i8, and a thread that owns a batch only folds eight limb sums per share.
-// profiles/r01_k2_tc.md showed that kernel bound by instruction issue (0.69 IPC with every pipe below its own
-// limit), so this one is the same dataflow with fewer instructions per batch:
-//
-//   * tiles come in PAIRS: MMA tile E holds the even batches of 256 consecutive ones, tile O the odd batches,
-//     so thread r owns the adjacent batches 2r and 2r + 1 -- its two results of a share row are ONE 16-byte
-//     store, its 2K secrets are K aligned 16-byte words of the raw vector which go into the operand tiles as they
-//     are (for odd K the middle word serves both rows; the constant operand has a zero where the neighbour's
-//     secret sits, hence two operand images, E and O);
-//   * the limbs of the constant operand are not 8 x 8 bits: widths (8,8,8,8,8,W5,8,13-W5) with W5 chosen per
-//     k + t so that  e0 + e1 2^16 + e2 2^32  fits one IMAD.WIDE whose addend is the register PAIR (e0, e2) and the
-//     top term folds with one mask and one shift -- 14 instructions per share and one wide multiply instead of
-//     16 and two (tests/test_k2_model.py restates it with Python integers and checks every bound);
-//   * store addresses are a uniform 64-bit base plus a 32-bit per-thread offset;
-//   * pass bookkeeping ((participant, pass) of the next unit, "does this pass lie inside the vector") is 32-bit and
-//     warp-uniform, and the MMAs are issued from warp-uniform code (elect.sync) with uniform descriptors.
-//
-// Shared memory per CTA (k=3, t=2, n=5): draws 2 x 8 KB, secrets 16 KB, two operand images 6 KB, raw secrets of
-// the coming pass 12 KB = 51 KB, four CTAs per SM (TMEM: two 64-column accumulators each).
-#include <algorithm>
-#include <cstring>
-
-#include "kernels.h"
-#include "tc_common.cuh"
+// packed_tc2.cu -- the paired-tile share-generation kernel (packed_tc2.cuh) instantiated for the shapes BASELINE names
+#include "packed_tc2.cuh"
 
 namespace sda {
 
-namespace {
-
-using namespace tc;
-
-constexpr int CTA2 = 128;            // threads = rows of one MMA tile = TMEM lanes
-
-constexpr int gcd_k(int a, int b) { return b == 0 ? a : gcd_k(b, a % b); }
-
-// width of limb 5 of the constant operand (see compose2): the widest for which e2 = d4 + 256 d5 stays below 2^29
-// when a limb sum has 8 (k + t) terms of at most 255 * (2^w - 1)
-constexpr int w5_for(int kt) {
-    for (int w5 = 8; w5 >= 5; w5--)
-        if ((long long)8 * kt * 255 * (255 + ((1ll << w5) - 1) * 256) < (1ll << 29)) return w5;
-    return 0;
-}
-
-struct LimbPlan {
-    int w[8], pos[8];
-};
-inline LimbPlan limb_plan(int kt) {
-    const int w5 = w5_for(kt);
-    LimbPlan lp{{8, 8, 8, 8, 8, w5, 8, 13 - w5}, {0, 8, 16, 24, 32, 40, 40 + w5, 48 + w5}};
-    return lp;
-}
-
-template <int K, int T, int N>
-struct Shape2 {
-    static_assert(T % 2 == 0 && T >= 2, "draws fill whole 16-byte chunks");
-    static constexpr int KT = K + T;
-    static constexpr int W5 = w5_for(KT);
-    static_assert(W5 >= 5, "k + t too large for the limb plan");
-    static constexpr int PAIRS = 4 / gcd_k(T, 4);            // tile pairs (256 batches each) per pass of a CTA
-    static constexpr int NB = T / gcd_k(T, 4);               // keystream blocks per thread per pass
-    static constexpr int PASS = PAIRS * 256;                 // batches per pass
-    static constexpr int DC = T / 2;                         // 16-byte chunks of a row holding draws
-    static constexpr int SC = (K + 1) / 2;                   // ... holding secrets
-    static constexpr int NKD = (DC + 1) / 2, NKS = (SC + 1) / 2;
-    static constexpr int NK = NKD + NKS;                     // MMAs per tile (32 bytes of K each)
-    // an odd chunk count lets the second chunk of the last K step alias the next 8-row group: B is 0 there
-    static constexpr uint32_t SBO_D = DC * 128, SBO_S = SC * 128;
-    static constexpr uint32_t D_TILE = 16 * SBO_D, S_TILE = 16 * SBO_S;
-    static constexpr uint32_t D_BYTES = PAIRS * 2 * D_TILE + 128, S_BYTES = PAIRS * 2 * S_TILE + 128;
-    static constexpr int NMMA = (8 * N + 15) / 16 * 16;
-    static constexpr uint32_t SBO_B = 2 * NK * 128;
-    static constexpr uint32_t B_IMG = NMMA / 8 * SBO_B;      // one operand image; the kernel holds two (E, O)
-    static constexpr uint32_t IN_BYTES = PASS * K * 8;       // the raw secrets of one pass
-    static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + 2 * B_IMG + IN_BYTES;
-    static constexpr int ACC_COLS = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : 128;
-    static constexpr int ACC_BUFS = 2 * ACC_COLS <= 128 ? 2 : 1;   // E and O side by side when four CTAs still fit
-    static constexpr int TMEM_COLS = ACC_BUFS * ACC_COLS;
-    static constexpr uint32_t IDESC = idesc_u8(NMMA);
-    static_assert(D_BYTES % 128 == 0 && S_BYTES % 128 == 0 && B_IMG % 16 == 0 && IN_BYTES % 16 == 0, "alignment");
-    static_assert(SMEM <= 227 * 1024 / 4 - 1024 || ACC_BUFS == 1, "four CTAs per SM");
-};
-
-#define SDA_QR2(a, b, c, d)                                     \
-    a += b; d ^= a; d = __funnelshift_l(d, d, 16);              \
-    c += d; b ^= c; b = __funnelshift_l(b, b, 12);              \
-    a += b; d ^= a; d = __funnelshift_l(d, d, 8);               \
-    c += d; b ^= c; b = __funnelshift_l(b, b, 7);
-
-// Columns 1..3 of the first round do not depend on the block counter while it stays below 2^32 (state words 13..15
-// are zero then): they are per-participant constants, computed once per launch by chacha_prepare_kernel and loaded
-// instead of being recomputed for every block -- 3 of a block's 8 ROUNDS / 2 quarter rounds.
-struct ChaChaPre {
-    uint32_t w[12];     // x1,x5,x9,x13, x2,x6,x10,x14, x3,x7,x11,x15 after the first column round, counter high word 0
-};
-
-__global__ void chacha_prepare_kernel(const ChaChaKey *__restrict__ keys, size_t P, ChaChaPre *__restrict__ pre) {
-    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= P) return;
-    const uint32_t c[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
-    const ChaChaKey k = keys[p];
-    for (int col = 1; col < 4; col++) {
-        uint32_t a = c[col], b = k.w[col], cc = k.w[4 + col], d = 0;
-        SDA_QR2(a, b, cc, d)
-        pre[p].w[4 * (col - 1) + 0] = a;
-        pre[p].w[4 * (col - 1) + 1] = b;
-        pre[p].w[4 * (col - 1) + 2] = cc;
-        pre[p].w[4 * (col - 1) + 3] = d;
-    }
-}
-
-// one keystream block (counter b0 < 2^32) from the key and its precomputed first-round columns
-template <int ROUNDS>
-__device__ __forceinline__ void chacha_block2(const uint32_t (&k)[8], const uint32_t (&pre)[12], uint32_t b0, uint32_t (&o)[16]) {
-    const uint32_t c0 = 0x61707865u, c1 = 0x3320646eu, c2 = 0x79622d32u, c3 = 0x6b206574u;
-    uint32_t x0 = c0, x4 = k[0], x8 = k[4], x12 = b0;
-    uint32_t x1 = pre[0], x5 = pre[1], x9 = pre[2], x13 = pre[3];
-    uint32_t x2 = pre[4], x6 = pre[5], x10 = pre[6], x14 = pre[7];
-    uint32_t x3 = pre[8], x7 = pre[9], x11 = pre[10], x15 = pre[11];
-    SDA_QR2(x0, x4, x8, x12)                   // the one column of round 1 that sees the counter
-#pragma unroll 3
-    for (int i = 0; i < ROUNDS / 2 - 1; i++) {  // diagonal round, then the next column round
-        SDA_QR2(x0, x5, x10, x15)
-        SDA_QR2(x1, x6, x11, x12)
-        SDA_QR2(x2, x7, x8, x13)
-        SDA_QR2(x3, x4, x9, x14)
-        SDA_QR2(x0, x4, x8, x12)
-        SDA_QR2(x1, x5, x9, x13)
-        SDA_QR2(x2, x6, x10, x14)
-        SDA_QR2(x3, x7, x11, x15)
-    }
-    SDA_QR2(x0, x5, x10, x15)
-    SDA_QR2(x1, x6, x11, x12)
-    SDA_QR2(x2, x7, x8, x13)
-    SDA_QR2(x3, x4, x9, x14)
-    o[0] = x0 + c0;     o[1] = x1 + c1;     o[2] = x2 + c2;      o[3] = x3 + c3;
-    o[4] = x4 + k[0];   o[5] = x5 + k[1];   o[6] = x6 + k[2];    o[7] = x7 + k[3];
-    o[8] = x8 + k[4];   o[9] = x9 + k[5];   o[10] = x10 + k[6];  o[11] = x11 + k[7];
-    o[12] = x12 + b0;   o[13] = x13;        o[14] = x14;         o[15] = x15;
-}
-
-// draw v = (hi word w0, lo word w1) -> a u64 congruent to v mod (p - 1) modulo p:  v mod (p - 1) = (v & p) + 2 (v >> 61)
-// unless that reaches p - 1, and v itself == (v & p) + (v >> 61) (mod p), so X = v + (v >> 61) serves as the operand row:
-// any u64 bit pattern is a valid row (the GEMM is linear in its bytes).  gen_range differs from this only when
-// v mod 2^61 >= 2^61 - 32 (a rejected word, a wrap-around of the reduction, or the overflow of this very sum).  The
-// necessary condition "bits 32..60 all ones" (2^-29 per draw) is accumulated as the running maximum of the masked
-// high words (one three-input VIMNMX per two draws), and the caller settles `suspect >= 2^29 - 1` exactly.
-__device__ __forceinline__ uint64_t reduce_draw2(uint32_t w0, uint32_t w1, uint32_t &suspect) {
-    uint32_t h;
-    asm("shr.u32 %0, %1, 29;" : "=r"(h) : "r"(w0));
-    suspect = max(suspect, w0 & LOW29);
-    return pack(w1, w0) + (uint64_t)h;
-}
-
-// canonical  sum_s d[s] 2^{pos[s]}  mod p  for the limb sums of one share (limb plan of k + t: positions
-// 0,8,16,24,32,40,40+W5,48+W5).  e0..e3 are 32-bit; X = e0 + e1 2^16 + e2 2^32 < 2^61 + 2^48 is one wide multiply
-// whose addend is the register pair (e0, e2); e3 2^{40+W5} == (e3 mod 2^{21-W5}) 2^{40+W5} + (e3 >> (21-W5)) because
-// 2^61 == 1; t = value + 1 lies in [1, 2^62) and the last four instructions are packed_tc.cu's.
-#ifndef SDA_TC2_XWIDE
-#define SDA_TC2_XWIDE 0      // 1: X by IMAD.WIDE with a run-time multiplier (one FMA-pipe instruction) instead of LEA + LEA.HI.X
-#endif
-#ifndef SDA_TC2_FINAL_X
-#define SDA_TC2_FINAL_X 1    // 1: the final 64-bit add takes its high addend from a register (IMAD.X) instead of a sign extension
-#endif
-template <int W5>
-__device__ __forceinline__ uint64_t compose2(const uint32_t (&d)[8], uint32_t two16) {
-    const uint32_t e0 = d[0] + (d[1] << 8), e1 = d[2] + (d[3] << 8);
-    const uint32_t e2 = d[4] + (d[5] << 8), e3 = d[6] + (d[7] << 8);
-    uint64_t x;
-#if SDA_TC2_XWIDE
-    // two16 == 65536 is a kernel parameter so that ptxas keeps the multiply (it turns a literal into two shifts-and-adds)
-    asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, %4, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1), "r"(two16));
-#else
-    asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, 65536, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1));
-#endif
-    constexpr uint32_t SH3 = 8 + W5;                                  // position of e3 inside the high word
-    const uint32_t m3 = (e3 << SH3) & (LOW29 & ~((1u << SH3) - 1u));
-    const uint32_t s3 = (e3 >> (21 - W5)) + 1u;                       // + 1: t == value + 1
-    const uint64_t t = x + pack(s3, m3);
-    uint32_t t_lo, t_hi;
-    unpack(t, t_lo, t_hi);
-    const uint32_t qm1 = (t_hi >> 29) - 1u;                           // floor((t - 1) / p) - 1 in {-1, 0} as two's complement
-    uint32_t r_lo, r_hi;
-#if SDA_TC2_FINAL_X
-    unpack(t + pack(qm1, qm1), r_lo, r_hi);                           // the 64-bit value -1 or 0: both words equal qm1
-#else
-    unpack(t + (uint64_t)(int64_t)(int32_t)qm1, r_lo, r_hi);
-#endif
-    return pack(r_lo, r_hi & LOW29);
-}
-
-// one elected lane of a converged warp: the NK MMAs of a 128-row tile into the accumulator at `taddr`
-template <class S>
-__device__ __forceinline__ void issue_tile2(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_img) {
-    const uint64_t dd = umma_desc(d_tile, S::SBO_D), ds = umma_desc(s_tile, S::SBO_S), db = umma_desc(b_img, S::SBO_B);
-#pragma unroll
-    for (int kk = 0; kk < S::NKD; kk++)
-        umma_i8(taddr, dd + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S::IDESC, kk > 0);
-#pragma unroll
-    for (int kk = 0; kk < S::NKS; kk++)
-        umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
-}
-__device__ __forceinline__ void commit2(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-// the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to.
-// Chunk gc of the pass (16 bytes = two draws, stream order) belongs to batch gc / DC of the pass; batch beta sits in
-// tile pair beta / 256, tile E or O by its parity, row (beta % 256) / 2.
-// a participant's key and first-round constants, loaded well ahead of the keystream that needs them (the loads are
-// the only global-memory latency on a pass's critical path)
-struct KeyRegs {
-    uint4 ka, kb, pa, pb, pc;
-};
-__device__ __forceinline__ KeyRegs load_keys2(const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, uint32_t p) {
-    const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
-    const uint4 *ps = reinterpret_cast<const uint4 *>(pres + p);
-    KeyRegs r;
-    r.ka = __ldg(src);
-    r.kb = __ldg(src + 1);
-    r.pa = __ldg(ps);
-    r.pb = __ldg(ps + 1);
-    r.pc = __ldg(ps + 2);
-    return r;
-}
-
-template <class S, int ROUNDS>
-__device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int tid, uint8_t *sD, unsigned *flag) {
-    uint32_t k[8], pre[12];
-    k[0] = kr.ka.x; k[1] = kr.ka.y; k[2] = kr.ka.z; k[3] = kr.ka.w;
-    k[4] = kr.kb.x; k[5] = kr.kb.y; k[6] = kr.kb.z; k[7] = kr.kb.w;
-    pre[0] = kr.pa.x; pre[1] = kr.pa.y; pre[2] = kr.pa.z; pre[3] = kr.pa.w;
-    pre[4] = kr.pb.x; pre[5] = kr.pb.y; pre[6] = kr.pb.z; pre[7] = kr.pb.w;
-    pre[8] = kr.pc.x; pre[9] = kr.pc.y; pre[10] = kr.pc.z; pre[11] = kr.pc.w;
-    const uint32_t blk0 = u * (uint32_t)(CTA2 * S::NB);           // the launcher keeps a participant below 2^32 blocks
-#pragma unroll 1
-    for (int nb = 0; nb < S::NB; nb++) {
-        const uint32_t slot = nb * CTA2 + tid;                    // block of this pass, in stream order
-        uint32_t w[16];
-        chacha_block2<ROUNDS>(k, pre, blk0 + slot, w);
-        uint32_t suspect = 0;
-        // the block's four chunks: chunk 0 goes to `dst`, the others to compile-time offsets from it
-        const uint32_t gc0 = slot * 4;
-        const uint32_t beta0 = gc0 / S::DC, c0 = gc0 % S::DC;
-        const uint32_t tile0 = (beta0 >> 8) * 2 + (beta0 & 1), row0 = (beta0 & 255) >> 1;
-        uint8_t *dst = sD + tile0 * S::D_TILE + (row0 >> 3) * S::SBO_D + c0 * LBO + (row0 & 7) * 16;
-#pragma unroll
-        for (int cb = 0; cb < 4; cb++) {                          // 4 chunks of 2 draws
-            const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1], suspect);
-            const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3], suspect);
-            // DC = 1: batches beta0 .. beta0 + 3 (beta0 a multiple of 4): tiles E, O, E, O, rows row0, row0, row0 + 1, row0 + 1
-            // DC = 2: batches beta0, beta0 + 1 (beta0 even): tiles E, E, O, O, chunks 0, 1, 0, 1 of row row0
-            // DC % 4 == 0: one batch, chunks c0 .. c0 + 3
-            static_assert(S::DC == 1 || S::DC == 2 || S::DC % 4 == 0, "draw chunks per batch");
-            const uint32_t delta = S::DC == 1 ? (cb & 1) * S::D_TILE + (cb >> 1) * 16
-                                 : S::DC == 2 ? (cb >> 1) * S::D_TILE + (cb & 1) * LBO
-                                              : cb * LBO;
-            uint32_t xal, xah, xbl, xbh;
-            unpack(xa, xal, xah);
-            unpack(xb, xbl, xbh);
-            *reinterpret_cast<uint4 *>(dst + delta) = make_uint4(xal, xah, xbl, xbh);
-        }
-        if (suspect >= LOW29) {
-            bool bad = false;
-#pragma unroll
-            for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xffffffe0u;
-            if (bad) atomicOr(flag, 1u);
-        }
-    }
-}
-
-// The raw secrets of pass (p, u) into the staging buffer by the threads themselves, zero beyond the vector
-// (batched.rs:38-43): the path of a pass that is not wholly inside the vector or whose source is not 16-byte aligned.
-// Every thread writes, and later reads, only its own 2K words per pair.
-template <class S, int K>
-__device__ __forceinline__ void fill_secrets2(const int64_t *__restrict__ secrets, size_t ld, size_t dim, uint32_t p, uint32_t u,
-                                              int tid, int64_t *sIn) {
-    const int64_t *sec = secrets + (size_t)p * ld;
-    const size_t e_first = ((size_t)u * S::PASS + 2 * tid) * K;
-#pragma unroll
-    for (int q = 0; q < S::PAIRS; q++) {
-        const size_t e0 = e_first + (size_t)q * (256 * K);
-#pragma unroll
-        for (int i = 0; i < 2 * K; i++) sIn[(q * 256 + 2 * tid) * K + i] = e0 + i < dim ? __ldg(sec + e0 + i) : 0;
-    }
-}
-
-// one thread: the whole pass -- PASS batches x K secrets, contiguous in the participant's vector -- into the staging
-// buffer with one bulk copy; completion (by byte count) on `bar`
-template <class S, int K>
-__device__ __forceinline__ void bulk_load_secrets2(const int64_t *__restrict__ secrets, size_t ld, uint32_t p, uint32_t u,
-                                                   uint32_t sin_addr, uint32_t bar) {
-    const int64_t *src = secrets + (size_t)p * ld + (size_t)u * (S::PASS * K);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(S::IN_BYTES) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(sin_addr), "l"(src), "r"(S::IN_BYTES), "r"(bar) : "memory");
-}
-
-__device__ __forceinline__ void canon_pair2(uint32_t &lo, uint32_t &hi) {
-    if ((int32_t)hi < 0) unpack(canon_negative((int64_t)pack(lo, hi)), lo, hi);
-}
-
-__device__ __forceinline__ void st_global_v2(char *ptr, uint64_t a, uint64_t b) {
-    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(ptr), "l"(a), "l"(b) : "memory");
-}
-__device__ __forceinline__ void st_global_1(char *ptr, uint64_t a) {
-    asm volatile("st.global.u64 [%0], %1;" :: "l"(ptr), "l"(a) : "memory");
-}
-
-// the odd batch's shares composed and both batches' shares stored: share row j of the pair at `off + j row_bytes`
-template <class S, int N>
-__device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint64_t (&re)[N], char *ptr, size_t row_bytes,
-                                           bool fast_store, uint32_t live, uint32_t two16) {
-    if (fast_store) {
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            st_global_v2(ptr, re[j], compose2<S::W5>(d[j], two16));
-            ptr += row_bytes;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            const uint64_t ro = compose2<S::W5>(d[j], two16);
-            if (live >= 1) st_global_1(ptr, re[j]);
-            if (live == 2) st_global_1(ptr + 8, ro);
-            ptr += row_bytes;
-        }
-    }
-}
-
-template <int K, int T, int N, int ROUNDS>
-__global__ void __launch_bounds__(CTA2, 1)
-packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
-                        uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
-                        const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,
-                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok, uint32_t two16) {
-    typedef Shape2<K, T, N> S;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *sD = smem;                                    // 2 x (PAIRS x {E, O} tiles x 128 rows x draws)
-    uint8_t *sS = smem + 2 * S::D_BYTES;                   // PAIRS x {E, O} tiles x 128 rows x secrets
-    uint8_t *sB = sS + S::S_BYTES;                         // the constant operand, E image then O image
-    int64_t *sIn = reinterpret_cast<int64_t *>(sB + 2 * S::B_IMG);   // the coming pass's raw secrets
-    __shared__ __align__(8) uint64_t mbar[3];              // [0] full (MMAs done), [1] drained (TMEM read out), [2] secrets landed
-    __shared__ uint32_t tmem_base;
-
-    const int tid = threadIdx.x;
-    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction, and known to be
-
-    // ---- one-time setup: TMEM, barriers, constant operand ------------------------------------
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     :: "r"(smem_u32(&tmem_base)), "n"(S::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&mbar[1])), "n"(CTA2) : "memory");
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[2])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (uint32_t i = tid; i < 2 * S::B_IMG / 16; i += CTA2) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t taddr = tmem_base;
-    const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
-    const uint32_t full_bar = smem_u32(&mbar[0]), drained_bar = smem_u32(&mbar[1]), landed_bar = smem_u32(&mbar[2]);
-    const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB), sin_addr = smem_u32(sIn);
-    uint32_t parity = 0, buf = 0, landed_parity = 0, dparity = 0;
-
-    // (participant, pass) of this CTA's units: unit x is pass unit_begin + x % units_per_p of participant x / units_per_p.
-    // All of it is 32-bit and the same in every thread.
-    const uint32_t step_p = gridDim.x / units_per_p, step_u = gridDim.x % units_per_p;
-    const uint32_t unit_end = unit_begin + units_per_p;
-    uint32_t p = blockIdx.x / units_per_p, u = unit_begin + blockIdx.x % units_per_p;
-    // a pass that lies wholly inside its vector arrives by bulk copy when the source is 16-byte aligned (bulk_ok)
-    auto by_bulk = [&](uint32_t uu) { return bulk_ok != 0 && uu < full_in_units; };
-
-    // output address of (p, u): share row 0, this thread's even batch of the pass's first pair.  A step adds step_p
-    // participants and step_u passes; when the pass index wraps, one participant more and units_per_p passes fewer.
-    char *opass = reinterpret_cast<char *>(out + (size_t)p * N * B + (size_t)u * S::PASS + 2 * tid);
-    const int64_t step_bytes = 8 * ((int64_t)step_p * N * (int64_t)B + (int64_t)step_u * S::PASS);
-    const int64_t wrap_bytes = 8 * ((int64_t)N * (int64_t)B - (int64_t)units_per_p * S::PASS);
-    if (blockIdx.x < units_total) {
-        if (by_bulk(u)) {
-            if (tid == 0) bulk_load_secrets2<S, K>(secrets, ld, p, u, sin_addr, landed_bar);
-        } else {
-            fill_secrets2<S, K>(secrets, ld, dim, p, u, tid, sIn);
-        }
-        stage_draws2<S, ROUNDS>(load_keys2(keys, pres, p), u, tid, sD, flag);
-    }
-
-    for (uint32_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
-        // this CTA's next unit; its key is requested now and used after the staging barrier
-        uint32_t pn = p + step_p, un = u + step_u;
-        if (un >= unit_end) {
-            un -= units_per_p;
-            pn++;
-        }
-        const bool more = unit + gridDim.x < units_total;
-        KeyRegs knext;
-        if (more) knext = load_keys2(keys, pres, pn);
-        // ---- this thread's 2K secrets of every pair (batches 2 tid, 2 tid + 1 of the pair): K aligned 16-byte words
-        //      of the raw vector, which are the operand chunks as they are -------------------------------------------
-        if (by_bulk(u)) {
-            mbar_wait(landed_bar, landed_parity);
-            landed_parity ^= 1;
-        }
-        uint4 v[S::PAIRS][K];                    // all loads first: their latency overlaps instead of adding up per pair
-#pragma unroll
-        for (int q = 0; q < S::PAIRS; q++) {
-            const uint4 *row = reinterpret_cast<const uint4 *>(sIn + (q * 256 + 2 * tid) * K);
-#pragma unroll
-            for (int i = 0; i < K; i++) v[q][i] = row[i];
-        }
-#pragma unroll
-        for (int q = 0; q < S::PAIRS; q++) {
-            uint32_t sign = 0;
-#pragma unroll
-            for (int i = 0; i < K; i++) sign |= v[q][i].y | v[q][i].w;
-            if ((int32_t)sign < 0) {
-#pragma unroll
-                for (int i = 0; i < K; i++) {
-                    canon_pair2(v[q][i].x, v[q][i].y);
-                    canon_pair2(v[q][i].z, v[q][i].w);
-                }
-            }
-            uint8_t *te = sS + (2 * q) * S::S_TILE + (tid >> 3) * S::SBO_S + (tid & 7) * 16;
-#pragma unroll
-            for (int c = 0; c < S::SC; c++) {
-                *reinterpret_cast<uint4 *>(te + c * LBO) = v[q][c];                          // E: words 0 .. SC-1
-                *reinterpret_cast<uint4 *>(te + S::S_TILE + c * LBO) = v[q][K - S::SC + c];  // O: words K-SC .. K-1
-            }
-        }
-        // rows complete: the secrets just written and the draws written during the previous pass
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_cur = d_base + buf * S::D_BYTES;
-        if (warp == 0) {
-            if (elect_one()) {
-                issue_tile2<S>(taddr, d_cur, s_base, b_base);
-                if constexpr (S::ACC_BUFS == 2) issue_tile2<S>(taddr + S::ACC_COLS, d_cur + S::D_TILE, s_base + S::S_TILE, b_base + S::B_IMG);
-                commit2(full_bar);
-                // everyone is past the barrier, i.e. has read this pass's raw secrets: the next pass's may land
-                if (more && by_bulk(un)) bulk_load_secrets2<S, K>(secrets, ld, pn, un, sin_addr, landed_bar);
-            }
-            __syncwarp();
-        }
-
-        // ---- the next pass's keystream, under this pass's first MMAs -----------------------------------
-        if (more) {
-            stage_draws2<S, ROUNDS>(knext, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
-            if (!by_bulk(un)) fill_secrets2<S, K>(secrets, ld, dim, pn, un, tid, sIn);
-        }
-
-        // ---- per pair: D = A . B^T on the tensor core, then compose the shares of batches 2 tid and 2 tid + 1 ------
-        // share row 0 of this thread's first pair of the pass
-        char *optr = opass;
-        const bool all_live = u < full_out_units;                             // every batch of the pass is below B
-        const size_t row_bytes = B * 8u;
-        const size_t pass_first = (size_t)u * S::PASS;
-#pragma unroll
-        for (int q = 0; q < S::PAIRS; q++) {
-            uint64_t re[N];
-            // batches of this thread that exist: 2 (both), 1 (only the even one) or 0
-            uint32_t live = 2;
-            if (!all_live) {
-                const size_t b_even = pass_first + (size_t)(q * 256 + 2 * tid);
-                live = b_even + 1 < B ? 2 : (b_even < B ? 1 : 0);
-            }
-            const bool fast_store = all_live && vec_ok != 0;                 // uniform: one 16-byte store per share row
-            if constexpr (S::ACC_BUFS == 2) {
-                mbar_wait(full_bar, parity);
-                parity ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                {
-                    uint32_t d[N][8];
-                    tmem_ld_shares<N>(my_taddr, d);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j], two16);
-                }
-                uint32_t d[N][8];
-                tmem_ld_shares<N>(my_taddr + S::ACC_COLS, d);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (q + 1 < S::PAIRS) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
-                    if (warp == 0) {
-                        mbar_wait(drained_bar, dparity);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (elect_one()) {
-                            issue_tile2<S>(taddr, d_cur + (2 * q + 2) * S::D_TILE, s_base + (2 * q + 2) * S::S_TILE, b_base);
-                            issue_tile2<S>(taddr + S::ACC_COLS, d_cur + (2 * q + 3) * S::D_TILE, s_base + (2 * q + 3) * S::S_TILE,
-                                           b_base + S::B_IMG);
-                            commit2(full_bar);
-                        }
-                        __syncwarp();
-                    }
-                    dparity ^= 1;
-                }
-                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live, two16);
-                optr += 256 * 8;
-            } else {
-                // one accumulator: E, then O into the same columns while E is being composed
-                mbar_wait(full_bar, parity);
-                parity ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                {
-                    uint32_t d[N][8];
-                    tmem_ld_shares<N>(my_taddr, d);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
-                    if (warp == 0) {
-                        mbar_wait(drained_bar, dparity);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (elect_one()) {
-                            issue_tile2<S>(taddr, d_cur + (2 * q + 1) * S::D_TILE, s_base + (2 * q + 1) * S::S_TILE, b_base + S::B_IMG);
-                            commit2(full_bar);
-                        }
-                        __syncwarp();
-                    }
-                    dparity ^= 1;
-#pragma unroll
-                    for (int j = 0; j < N; j++) re[j] = compose2<S::W5>(d[j], two16);
-                }
-                mbar_wait(full_bar, parity);
-                parity ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint32_t d[N][8];
-                tmem_ld_shares<N>(my_taddr, d);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (q + 1 < S::PAIRS) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
-                    if (warp == 0) {
-                        mbar_wait(drained_bar, dparity);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (elect_one()) {
-                            issue_tile2<S>(taddr, d_cur + (2 * q + 2) * S::D_TILE, s_base + (2 * q + 2) * S::S_TILE, b_base);
-                            commit2(full_bar);
-                        }
-                        __syncwarp();
-                    }
-                    dparity ^= 1;
-                }
-                store_pair<S, N>(d, re, optr, row_bytes, fast_store, live, two16);
-                optr += 256 * 8;
-            }
-        }
-        // every thread is past its TMEM loads of the last pair and every MMA of this pass has completed
-        // (`full` was waited on), so the next pass may overwrite the secrets and reuse TMEM
-        // the same address for the next unit, by the difference (64-bit multiplies stay out of the loop)
-        opass += (un < u ? wrap_bytes : 0) + step_bytes;
-        p = pn;
-        u = un;
-        buf ^= 1;
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(S::TMEM_COLS) : "memory");
-}
-
-// the constant operand as it lies in shared memory: image E (rows = even batches of a pair) then image O
-template <int K, int T, int N>
-void build_b_image2(const Matrix &m, uint64_t p, uint8_t *img) {
-    typedef Shape2<K, T, N> S;
-    typedef unsigned __int128 u128;
-    const LimbPlan lp = limb_plan(K + T);
-    memset(img, 0, 2 * S::B_IMG);
-    for (int par = 0; par < 2; par++)
-        for (int j = 0; j < N; j++)
-            for (int part = 0; part < 2; part++)                // 0: draws (K steps 0..NKD), 1: secrets (the rest)
-                for (int c = 0; c < (part ? S::SC : S::DC); c++)
-                    for (int v = 0; v < 2; v++) {
-                        // draw / secret index within the batch: an odd row of an odd-K pair starts half a chunk late
-                        const int idx = 2 * c + v - ((part && par && (K & 1)) ? 1 : 0);
-                        if (idx < 0 || idx >= (part ? K : T)) continue;
-                        const int xi = part ? idx : K + idx;        // index into x = [secrets ; randomness]
-                        const int cg = part ? 2 * S::NKD + c : c;   // chunk along K of the whole row
-                        for (int byte = 0; byte < 8; byte++) {
-                            const uint64_t cst = (uint64_t)((u128)m.e[j * (K + T) + xi] * ((((u128)1) << (8 * byte)) % p) % p);
-                            for (int s = 0; s < 8; s++) {
-                                const int n = j * 8 + s;
-                                img[par * S::B_IMG + (n / 8) * S::SBO_B + cg * LBO + (n % 8) * 16 + v * 8 + byte] =
-                                    (uint8_t)((cst >> lp.pos[s]) & ((1u << lp.w[s]) - 1u));
-                            }
-                        }
-                    }
-}
-
-template <int K, int T, int N, int ROUNDS>
-cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
-                    size_t n_batches, const ChaChaKey *keys, uint32_t *d_pre, const uint8_t *d_b_image, int64_t *out,
-                    unsigned *flag) {
-    typedef Shape2<K, T, N> S;
-    const size_t B = (dim + K - 1) / K;
-    if (first_batch % S::PASS != 0 || first_batch > B) return cudaErrorInvalidValue;
-    if (n_batches > B - first_batch) n_batches = B - first_batch;
-    const size_t unit_begin = first_batch / S::PASS;
-    const size_t units_per_p = (n_batches + S::PASS - 1) / S::PASS;
-    const size_t units_total = units_per_p * P;
-    if (units_total == 0) return cudaSuccess;
-    if ((unit_begin + units_per_p) >> 31 || units_total >> 31 || P >> 31) return cudaErrorInvalidValue;
-    auto kern = packed_share_tc2_kernel<K, T, N, ROUNDS>;
-    // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh)
-    const size_t smem = smem_capping_residency(S::SMEM, 512 / S::TMEM_COLS);
-    static KernelSetup setup;
-    int regs = 0;
-    size_t static_smem = 0;
-    const cudaError_t se = setup_kernel(setup, kern, smem, &regs, &static_smem);
-    if (se != cudaSuccess) return se;
-    const int per_sm = resident_ctas(regs, CTA2, smem, static_smem, S::TMEM_COLS);
-    size_t grid = (size_t)lc.sm_count * per_sm;
-    if (grid > units_total) grid = units_total;
-    // bulk copies need 16-byte aligned sources: every pass of every participant starts at an even element
-    const int bulk_ok = reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
-    // 16-byte stores need every share row to start at an even element
-    const int vec_ok = reinterpret_cast<uintptr_t>(out) % 16 == 0 && B % 2 == 0;
-    const size_t full_in = dim / ((size_t)S::PASS * K), full_out = B / S::PASS;
-    // a participant's keystream stays below 2^32 blocks (B T / 8 of them): the counter's high word is 0
-    if ((B * (size_t)T + 7) / 8 >> 32) return cudaErrorInvalidValue;
-    ChaChaPre *pres = reinterpret_cast<ChaChaPre *>(d_pre);
-    chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
-    ++*lc.nlaunch;
-    kern<<<(unsigned)grid, CTA2, smem, lc.stream>>>(secrets, ld, dim, B, (uint32_t)unit_begin, (uint32_t)units_per_p,
-                                                    (uint32_t)units_total, (uint32_t)std::min<size_t>(full_in, 0xffffffffu),
-                                                    (uint32_t)std::min<size_t>(full_out, 0xffffffffu), keys, pres,
-                                                    reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok, 65536u);
-    ++*lc.nlaunch;
-    return cudaGetLastError();
-}
-
-}  // namespace
-
 #define SDA_TC2_SHAPES(X) X(3, 2, 5) X(5, 4, 9) X(3, 4, 7) X(3, 4, 8)
 
-// shapes and sizes this kernel serves: p = 2^61 - 1 and every share row (n B i64 per participant) within 32-bit
-// byte offsets of the pass's first batch
+// shapes and sizes this instantiation serves (p = 2^61 - 1)
 bool packed_share_tc2_supported(int k, int t, int n, size_t dim) {
     const size_t B = (dim + (size_t)k - 1) / (size_t)k;
-    if ((size_t)n * B * 8 + (1u << 16) >= (1ull << 32)) return false;
+    if ((B * (size_t)t + 7) / 8 >> 32) return false;     // a participant's keystream stays below 2^32 blocks
 #define X(K, T, N) if (k == K && t == T && n == N) return true;
     SDA_TC2_SHAPES(X)
 #undef X

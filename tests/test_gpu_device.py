@@ -68,6 +68,35 @@ def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
         ctx.set_packed_path(0)
 
 
+@pytest.mark.parametrize("shape", [(4, 2, 6), (2, 4, 8), (8, 2, 3), (1, 4, 5), (7, 4, 7), (3, 2, 6)])
+@pytest.mark.parametrize("offset,ld_pad", [(0, 0), (1, 1)])
+def test_paired_tile_kernel_with_run_time_share_count(ctx, oracle, torch_cuda, shape, offset, ld_pad):
+    """packed_tc2n.cu: (k, t) templated, n <= 8 at run time, over 2^61-1: several participants, aligned (bulk copy, 16-byte
+    stores) and unaligned sources, vectors ending inside a pass, negative secrets -- every share against the oracle"""
+    t = torch_cuda
+    k, tt, n = shape
+    s = util.packed_scheme(P61, k, tt, n, oracle)
+    rng = np.random.default_rng(k * 10 + tt + n)
+    for P, dim in [(1, 2), (3, 5 * 512 * k + 2 * k + 1), (2, 1024 * k)]:
+        ld = dim + (dim & 1) + ld_pad
+        B = s.batches(dim)
+        secrets = rng.integers(0, P61, size=(P, dim), dtype=np.int64)
+        secrets[-1, ::7] = rng.integers(-(1 << 63), 1 << 63, size=secrets[-1, ::7].shape, dtype=np.int64)
+        flat = np.zeros(offset + P * ld, dtype=np.int64)
+        for pi in range(P):
+            flat[offset + pi * ld: offset + pi * ld + dim] = secrets[pi]
+        d_in = dev(t, flat)[offset:]
+        seeds = b"".join(util.seed_bytes(f"tc2n/{shape}/{P}/{dim}/{pi}") for pi in range(P))
+        d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
+        ctx.share_generate_dev(s, d_in, ld, P, dim, seeds, d_out)
+        ctx.synchronize()
+        assert "at run time" in ctx.last_kernel() and "tcgen05" in ctx.last_kernel(), ctx.last_kernel()
+        got = host(d_out)
+        for pi in range(P):
+            exp = util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)
+            assert np.array_equal(got[pi], util.canon(oracle, P61, exp)), (shape, P, dim, pi)
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 6), (7, 5, 16), (1, 1, 2), (4, 1, 9), (9, 7, 32)])
 @pytest.mark.parametrize("p", [P61, params.P61_GENERIC])
 def test_runtime_shaped_kernel_many_participants(ctx, oracle, torch_cuda, shape, p):

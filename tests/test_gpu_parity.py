@@ -175,7 +175,9 @@ def test_packed_generate_literal_oracle(ctx, oracle):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 3), (2, 3, 6), (4, 3, 10), (7, 5, 16), (2, 1, 4), (8, 8, 20), (15, 1, 17), (1, 15, 32),
-                                   (3, 3, 7), (6, 7, 14), (5, 2, 9)])
+                                   (3, 3, 7), (6, 7, 14), (5, 2, 9),
+                                   # k <= 8, t in {2, 4}, n <= 8 over 2^61-1: the paired-tile kernel with n at run time
+                                   (4, 2, 6), (2, 4, 8), (8, 4, 5), (1, 2, 3), (6, 2, 7), (7, 4, 8), (8, 2, 1), (3, 2, 4)])
 @pytest.mark.parametrize("p", [P61, PGEN, 2305843009213693561])
 def test_packed_generate_generic_shapes(ctx, oracle, shape, p):
     """any (k, t, n) the reference accepts (packed_shamir.rs:13-27) runs on the run-time-shaped tcgen05 kernel: odd t,
@@ -192,7 +194,10 @@ def test_packed_generate_generic_shapes(ctx, oracle, shape, p):
             seed = util.seed_bytes(f"gen/{shape}/{dim}/{kind}")
             exp = util.oracle_generate(oracle, s, secrets, seed, matrix=True)
             assert np.array_equal(ctx.share_generate(s, secrets, seed), exp), (shape, p, dim, kind)
-    assert "run-time shape" in ctx.last_kernel() and "tcgen05" in ctx.last_kernel()
+    name = ctx.last_kernel()
+    assert "tcgen05" in name and ("run-time shape" in name or "at run time" in name), name
+    k_, t_, n_ = shape
+    assert ("at run time" in name) == (p == P61 and k_ <= 8 and t_ in (2, 4) and n_ <= 8), name
 
 
 def test_packed_share_matrix_matches_oracle(ctx, oracle):

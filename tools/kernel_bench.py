@@ -148,7 +148,7 @@ def main():
             print(json.dumps({"kernel": "packed_share generic prime", "skipped": str(e)}), flush=True)
 
         # ---- shapes without a templated kernel: the run-time-shaped tcgen05 kernel (packed_tcg.cu) ---------------------
-        for k_, t_, n_ in ((3, 2, 6), (3, 3, 7), (5, 4, 10), (8, 8, 20)):
+        for k_, t_, n_ in ((3, 2, 6), (3, 2, 4), (5, 4, 8), (4, 2, 8), (3, 3, 7), (5, 4, 10), (8, 8, 20)):
             s = params.LinearSecretSharingScheme.PackedShamir(k_, n_, t_, P61, params.ROOT_ORDER_31, params.ROOT_ORDER_41)
             P, dim = 64, 10_000_000
             B = s.batches(dim)
@@ -156,7 +156,7 @@ def main():
             ctx.synth_fill_dev(10, P61, 0, P * dim, sec)
             sh = empty(P, n_, B)
             sd = seeds(f"rt{k_}{t_}{n_}", P)
-            timeit(f"packed_share k={k_} t={t_} n={n_} [{P}][10M] (run-time-shaped tensor-core kernel)",
+            timeit(f"packed_share k={k_} t={t_} n={n_} [{P}][10M] (no fully templated kernel)",
                    lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n_ * B) * 8,
                    f"8(1+n/k) = {8 * (1 + n_ / k_):.2f} B per secret")
             del sec, sh
