@@ -104,9 +104,10 @@ int         sda_ctx_get_rng_rounds(const sda_ctx *ctx);
  * shapes, reconstruction for k, m' <= 16): the tcgen05 (tensor-core, byte-limb GEMM) ones or the
  * CUDA-core ones.  All are exact and produce identical results; AUTO picks the tensor-core kernels.
  * TENSOR_CORES_V1 keeps share generation on the first-generation tensor-core kernel (one batch per thread
- * and tile) instead of the paired-tile one, for side-by-side measurements. */
+ * and tile) instead of the paired-tile one, and TENSOR_CORES_ANY_SHAPE sends even the instantiated shapes to the
+ * kernels that serve every other (k, t, n); both for side-by-side measurements. */
 enum { SDA_PACKED_PATH_AUTO = 0, SDA_PACKED_PATH_CUDA_CORES = 1, SDA_PACKED_PATH_TENSOR_CORES = 2,
-       SDA_PACKED_PATH_TENSOR_CORES_V1 = 3 };
+       SDA_PACKED_PATH_TENSOR_CORES_V1 = 3, SDA_PACKED_PATH_TENSOR_CORES_ANY_SHAPE = 4 };
 int         sda_ctx_set_packed_path(sda_ctx *ctx, int path);
 /* stream (cudaStream_t) the *_dev entry points launch on; default: a context-owned stream */
 int         sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream);

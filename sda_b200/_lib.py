@@ -14,6 +14,7 @@ SDA_OK, SDA_ERR_INVALID, SDA_ERR_CUDA, SDA_ERR_NCCL, SDA_ERR_UNSUPPORTED = 0, 1,
 SHARING_ADDITIVE, SHARING_PACKED_SHAMIR = 0, 1
 MASK_NONE, MASK_FULL, MASK_CHACHA = 0, 1, 2
 PACKED_PATH_AUTO, PACKED_PATH_CUDA_CORES, PACKED_PATH_TENSOR_CORES, PACKED_PATH_TENSOR_CORES_V1 = 0, 1, 2, 3
+PACKED_PATH_TENSOR_CORES_ANY_SHAPE = 4
 
 
 class sda_sharing_scheme(C.Structure):

@@ -499,7 +499,7 @@ int ensure_tc_image(sda_ctx *ctx, const Packed &pk, const Matrix &M) {
 enum { TC_NONE = 0, TC_V1 = 1, TC_PAIRED = 2, TC_RUNTIME = 3, TC_PAIRED_RTN = 4 };
 int tc_kernel_for(const sda_ctx *ctx, const Packed &pk, size_t dim) {
     if (ctx->packed_path == SDA_PACKED_PATH_CUDA_CORES) return TC_NONE;
-    if (packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
+    if (ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_ANY_SHAPE && packed_share_tc_image_bytes(pk.k, pk.t, pk.n) != 0) {
         if (pk.p == P61 && ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 && packed_share_tc2_supported(pk.k, pk.t, pk.n, dim))
             return TC_PAIRED;
         return TC_V1;
@@ -524,7 +524,7 @@ int ensure_image(sda_ctx *ctx, int which, const Packed &pk, const Matrix &M, Dev
     key.insert(key.end(), M.e, M.e + M.rows * M.cols);
     if (key == *cached) return SDA_OK;
     const size_t ib = which == TC_PAIRED ? packed_share_tc2_image_bytes(pk.k, pk.t, pk.n)
-                    : which == TC_PAIRED_RTN ? packed_share_tc2n_image_bytes(pk.k, pk.t)
+                    : which == TC_PAIRED_RTN ? packed_share_tc2n_image_bytes(pk.k, pk.t, pk.n)
                                              : packed_share_tcg_image_bytes(pk.k, pk.t, pk.n);
     std::vector<uint8_t> img(ib);
     if (which == TC_PAIRED) packed_share_tc2_build_image(pk.k, pk.t, pk.n, M, pk.p, img.data());
@@ -998,7 +998,7 @@ int sda_ctx_get_rng_rounds(const sda_ctx *ctx) { return ctx ? ctx->rounds : 0; }
 int sda_ctx_set_packed_path(sda_ctx *ctx, int path) {
     if (!ctx) return SDA_ERR_INVALID;
     if (path != SDA_PACKED_PATH_AUTO && path != SDA_PACKED_PATH_CUDA_CORES && path != SDA_PACKED_PATH_TENSOR_CORES &&
-        path != SDA_PACKED_PATH_TENSOR_CORES_V1)
+        path != SDA_PACKED_PATH_TENSOR_CORES_V1 && path != SDA_PACKED_PATH_TENSOR_CORES_ANY_SHAPE)
         return fail(ctx, SDA_ERR_INVALID, "unknown packed-share path %d", path);
     ctx->packed_path = path;
     return SDA_OK;

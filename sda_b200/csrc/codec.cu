@@ -5,10 +5,11 @@
 // 7 bits per byte, least significant group first, MSB = continuation; values are concatenated with no length
 // prefix.  A 61-bit share takes 9 bytes, an arbitrary i64 at most 10.
 //
-// Both directions are variable-length, so each is a count / scan / write sequence over fixed chunks of the
-// input; the per-chunk totals are scanned by one CTA (`codec_scan_kernel`), everything else is one thread per
-// few elements.  The byte streams move through shared memory so that global traffic is 16-byte vectors in
-// both directions whatever the byte alignment of a chunk's first value:
+// Both directions are variable-length, so each CTA needs the total of every chunk before its own.  One launch per
+// direction: a CTA takes the next chunk (a ticket, so that every earlier chunk is already running), sizes it, publishes
+// its total, and gets its offset by looking back over its predecessors' published totals / running prefixes
+// (`chunk_offset`, a chained scan); the input is read once.  The byte streams move through shared memory so that
+// global traffic is 16-byte vectors in both directions whatever the byte alignment of a chunk's first value:
 //   encode: read 8 n (i64), write <= 10 n bytes;   decode: read the bytes, write 8 n.
 // The sealed box around the encoded bytes (libsodium) is out of scope and stays on the CPU.
 #include "kernels.h"
@@ -52,24 +53,66 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t *t
     return base + incl - x;
 }
 
-// ---- encode -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA)
-varint_count_kernel(const int64_t *__restrict__ in, size_t n, uint64_t *__restrict__ chunk_bytes) {
-    const size_t e0 = (size_t)blockIdx.x * ECHUNK + (size_t)threadIdx.x * EPT;
-    uint32_t bytes = 0;
-#pragma unroll
-    for (int i = 0; i < EPT; i++)
-        if (e0 + i < n) bytes += varint_len(zigzag(__ldg(in + e0 + i)));
-    uint32_t total;
-    block_exclusive_scan(bytes, &total);
-    if (threadIdx.x == 0) chunk_bytes[blockIdx.x] = total;
+// ---- chained scan over chunks -------------------------------------------------------------------------------
+// scratch: state[0 .. chunks) (zeroed before the launch), then the ticket counter (zeroed), then the grand total.
+// A state word is a 62-bit count tagged TOTAL (this chunk alone) or PREFIX (this chunk and everything before it).
+constexpr uint64_t TAG_TOTAL = 1ull << 62, TAG_PREFIX = 2ull << 62, COUNT_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ uint64_t ld_state(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(uint64_t *p, uint64_t v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
+// the next chunk in launch order (uniform across the CTA)
+__device__ __forceinline__ uint32_t take_chunk(uint64_t *ticket) {
+    __shared__ uint32_t chunk_s;
+    if (threadIdx.x == 0) chunk_s = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long *>(ticket), 1ull);
+    __syncthreads();
+    return chunk_s;
+}
+
+// sum of the totals of chunks 0 .. chunk-1, given this chunk's own; called by every thread, the look-back runs in warp 0.
+// The last chunk leaves the grand total in *grand.
+__device__ __forceinline__ uint64_t chunk_offset(uint64_t *state, uint32_t chunk, uint32_t chunks, uint32_t my_total, uint64_t *grand) {
+    __shared__ uint64_t offset_s;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        if (lane == 0 && chunk > 0) st_state(state + chunk, TAG_TOTAL | my_total);
+        uint64_t prefix = 0;
+        for (int64_t first = (int64_t)chunk - 1; first >= 0; first -= 32) {
+            const int64_t j = first - lane;
+            uint64_t v;
+            do {
+                v = j >= 0 ? ld_state(state + j) : TAG_PREFIX;          // before chunk 0: an empty prefix
+            } while (__any_sync(0xffffffffu, (v >> 62) == 0));
+            const unsigned prefixes = __ballot_sync(0xffffffffu, (v >> 62) == 2);
+            const int stop = prefixes ? __ffs(prefixes) - 1 : 31;        // the nearest chunk that already knows its prefix
+            uint64_t part = lane <= stop ? (v & COUNT_MASK) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            prefix += part;
+            if (prefixes) break;
+        }
+        if (lane == 0) {
+            st_state(state + chunk, TAG_PREFIX | (prefix + my_total));
+            offset_s = prefix;
+            if (chunk + 1 == chunks) *grand = prefix + my_total;
+        }
+    }
+    __syncthreads();
+    return offset_s;
+}
+
+// ---- encode -------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA)
-varint_write_kernel(const int64_t *__restrict__ in, size_t n, const uint64_t *__restrict__ chunk_off,
-                    uint8_t *__restrict__ out) {
+varint_encode_kernel(const int64_t *__restrict__ in, size_t n, uint32_t chunks, uint64_t *state, uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t stage[EBYTES];
-    const size_t e0 = (size_t)blockIdx.x * ECHUNK + (size_t)threadIdx.x * EPT;
+    const uint32_t chunk = take_chunk(state + chunks);
+    const size_t e0 = (size_t)chunk * ECHUNK + (size_t)threadIdx.x * EPT;
     uint64_t z[EPT];
     uint32_t bytes = 0;
 #pragma unroll
@@ -79,7 +122,7 @@ varint_write_kernel(const int64_t *__restrict__ in, size_t n, const uint64_t *__
     }
     uint32_t total;
     const uint32_t local = block_exclusive_scan(bytes, &total);
-    const uint64_t goff = chunk_off[blockIdx.x];
+    const uint64_t goff = chunk_offset(state, chunk, chunks, total, state + chunks + 1);
     const uint32_t phase = (uint32_t)((uintptr_t)(out + goff) & 15);    // stage with the destination's 16-byte phase
     uint32_t w = phase + local;
 #pragma unroll
@@ -128,17 +171,6 @@ __device__ __forceinline__ void stage_chunk(const uint8_t *__restrict__ buf, siz
     if (threadIdx.x < HALO) stage[threadIdx.x] = c0 >= HALO - threadIdx.x ? __ldg(buf + c0 - HALO + threadIdx.x) : 0x00;
 }
 
-__global__ void __launch_bounds__(CTA)
-varint_term_count_kernel(const uint8_t *__restrict__ buf, size_t len, uint64_t *__restrict__ chunk_values) {
-    __shared__ __align__(16) uint8_t stage[HALO + DCHUNK];
-    stage_chunk(buf, len, (size_t)blockIdx.x * DCHUNK, stage);
-    __syncthreads();
-    const uint32_t cnt = terminators16(*reinterpret_cast<const uint4 *>(stage + HALO + threadIdx.x * DPT));
-    uint32_t total;
-    block_exclusive_scan(cnt, &total);
-    if (threadIdx.x == 0) chunk_values[blockIdx.x] = total;
-}
-
 // 7-bit groups of up to 10 little-endian bytes (lo = bytes 0..7, hi = bytes 8..9) -> 64-bit integer
 __device__ __forceinline__ uint64_t squeeze_leb128(uint64_t lo, uint32_t hi) {
     uint64_t x = lo & 0x7f7f7f7f7f7f7f7full;
@@ -153,11 +185,12 @@ __device__ __forceinline__ uint64_t squeeze_leb128(uint64_t lo, uint32_t hi) {
 // Two phases per chunk so that neither diverges: every thread lists the terminator positions of its 16 bytes
 // (prefix positions from a block scan), then thread v decodes value v of the chunk from a 10-byte window.
 __global__ void __launch_bounds__(CTA)
-varint_decode_kernel(const uint8_t *__restrict__ buf, size_t len, const uint64_t *__restrict__ chunk_first, size_t cap,
+varint_decode_kernel(const uint8_t *__restrict__ buf, size_t len, uint32_t chunks, uint64_t *state, size_t cap,
                      int64_t *__restrict__ out, unsigned *status) {
     __shared__ __align__(16) uint8_t stage[HALO + DCHUNK + 16];
     __shared__ uint16_t ends[DCHUNK];                       // chunk-relative position of every terminator, in order
-    const size_t c0 = (size_t)blockIdx.x * DCHUNK;
+    const uint32_t cid = take_chunk(state + chunks);
+    const size_t c0 = (size_t)cid * DCHUNK;
     stage_chunk(buf, len, c0, stage);
     if (threadIdx.x < 16) stage[HALO + DCHUNK + threadIdx.x] = 0x80;
     __syncthreads();
@@ -175,7 +208,7 @@ varint_decode_kernel(const uint8_t *__restrict__ buf, size_t len, const uint64_t
     for (uint32_t m = mask; m; m &= m - 1) ends[slot++] = (uint16_t)(threadIdx.x * DPT + __ffs(m) - 1);
     __syncthreads();
     unsigned bad = 0;
-    const uint64_t k0 = chunk_first[blockIdx.x];
+    const uint64_t k0 = chunk_offset(state, cid, chunks, total, state + chunks + 1);     // values that end before this chunk
     for (uint32_t v = threadIdx.x; v < total; v += CTA) {
         const int end = ends[v];
         int start;
@@ -212,69 +245,32 @@ varint_decode_kernel(const uint8_t *__restrict__ buf, size_t len, const uint64_t
     if (bad) atomicOr(status, bad);
 }
 
-// single-CTA exclusive scan of counts[0..n) in place; total -> counts[n]
-__global__ void __launch_bounds__(1024) codec_scan_kernel(uint64_t *counts, size_t n) {
-    __shared__ uint64_t wsum[32];
-    __shared__ uint64_t carry_s, total_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (size_t base = 0; base < n; base += 1024) {
-        const size_t i = base + threadIdx.x;
-        const uint64_t x = i < n ? counts[i] : 0;
-        uint64_t incl = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
-        }
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint64_t t = wsum[lane];
-            uint64_t ti = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t y = __shfl_up_sync(0xffffffffu, ti, o);
-                if (lane >= o) ti += y;
-            }
-            wsum[lane] = ti - t;
-            if (lane == 31) total_s = ti;
-        }
-        __syncthreads();
-        if (i < n) counts[i] = carry_s + wsum[warp] + incl - x;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s += total_s;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) counts[n] = carry_s;
-}
-
 }  // namespace
 
-size_t varint_encode_scratch_elems(size_t n) { return (n + ECHUNK - 1) / ECHUNK + 1; }
-size_t varint_decode_scratch_elems(size_t len) { return (len + DCHUNK - 1) / DCHUNK + 1; }
+// state per chunk, the ticket, the total
+size_t varint_encode_scratch_elems(size_t n) { return (n + ECHUNK - 1) / ECHUNK + 2; }
+size_t varint_decode_scratch_elems(size_t len) { return (len + DCHUNK - 1) / DCHUNK + 2; }
 
-// out needs 10 n bytes; the encoded length lands in scratch[chunks] (device) for the caller to read back
+// out needs 10 n bytes; the encoded length lands in the last scratch element (device) for the caller to read back
 cudaError_t launch_varint_encode(const LaunchCtx &lc, const int64_t *in, size_t n, uint8_t *out, uint64_t *scratch) {
     const size_t chunks = (n + ECHUNK - 1) / ECHUNK;
-    if (chunks == 0) return cudaMemsetAsync(scratch, 0, sizeof(uint64_t), lc.stream);
-    varint_count_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(in, n, scratch);
-    codec_scan_kernel<<<1, 1024, 0, lc.stream>>>(scratch, chunks);
-    varint_write_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(in, n, scratch, out);
-    *lc.nlaunch += 3;
+    if (chunks >> 31) return cudaErrorInvalidValue;
+    const cudaError_t e = cudaMemsetAsync(scratch, 0, (chunks + 2) * sizeof(uint64_t), lc.stream);
+    if (e != cudaSuccess || chunks == 0) return e;
+    varint_encode_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(in, n, (uint32_t)chunks, scratch, out);
+    ++*lc.nlaunch;
     return cudaGetLastError();
 }
 
-// the value count lands in scratch[chunks]; *status (device, pre-cleared) gets the malformed-stream bits
+// the value count lands in the last scratch element; *status (device, pre-cleared) gets the malformed-stream bits
 cudaError_t launch_varint_decode(const LaunchCtx &lc, const uint8_t *buf, size_t len, int64_t *out, size_t cap,
                                  uint64_t *scratch, unsigned *status) {
     const size_t chunks = (len + DCHUNK - 1) / DCHUNK;
-    if (chunks == 0) return cudaMemsetAsync(scratch, 0, sizeof(uint64_t), lc.stream);
-    varint_term_count_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(buf, len, scratch);
-    codec_scan_kernel<<<1, 1024, 0, lc.stream>>>(scratch, chunks);
-    varint_decode_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(buf, len, scratch, cap, out, status);
-    *lc.nlaunch += 3;
+    if (chunks >> 31) return cudaErrorInvalidValue;
+    const cudaError_t e = cudaMemsetAsync(scratch, 0, (chunks + 2) * sizeof(uint64_t), lc.stream);
+    if (e != cudaSuccess || chunks == 0) return e;
+    varint_decode_kernel<<<(unsigned)chunks, CTA, 0, lc.stream>>>(buf, len, (uint32_t)chunks, scratch, cap, out, status);
+    ++*lc.nlaunch;
     return cudaGetLastError();
 }
 

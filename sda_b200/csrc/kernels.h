@@ -109,10 +109,10 @@ size_t packed_share_tc2_key_scratch_bytes(size_t P);
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
                                     uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
-// the same kernel with the share count n <= 8 as a run-time value, per (k, t) with k <= 8, t in {2, 4} (packed_tc2n.cu);
+// the same kernel with the share count n <= 32 as a run-time value, per (k, t) with k <= 8, t <= 8 (packed_tc2n.cu);
 // 2^61 - 1 and 20 rounds only
 bool packed_share_tc2n_supported(int k, int t, int n, size_t dim, int rounds);
-size_t packed_share_tc2n_image_bytes(int k, int t);
+size_t packed_share_tc2n_image_bytes(int k, int t, int n);
 void packed_share_tc2n_build_image(int k, int t, int n, const Matrix &mtx, uint64_t p, uint8_t *img);
 size_t packed_share_tc2n_slice_batches(int k, int t);
 cudaError_t launch_packed_share_tc2n(const LaunchCtx &lc, int k, int t, int n, const int64_t *secrets, size_t ld, size_t P,

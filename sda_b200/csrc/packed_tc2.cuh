@@ -36,6 +36,7 @@ namespace {
 using namespace tc;
 
 constexpr int CTA2 = 128;            // threads = rows of one MMA tile = TMEM lanes
+constexpr int SDA_TC2_MAX_GROUPS = 4;  // run-time share count: up to 4 groups of 8 shares
 
 constexpr int gcd_k(int a, int b) { return b == 0 ? a : gcd_k(b, a % b); }
 
@@ -58,22 +59,32 @@ inline LimbPlan limb_plan(int kt) {
 
 template <int K, int T, int N>
 struct Shape2 {
-    static_assert(T % 2 == 0 && T >= 2, "draws fill whole 16-byte chunks");
+    static_assert(T >= 1, "at least one draw per batch");
+    static constexpr int TT = T;
     static constexpr int KT = K + T;
     static constexpr int W5 = w5_for(KT);
     static_assert(W5 >= 5, "k + t too large for the limb plan");
-    static constexpr int PAIRS = 4 / gcd_k(T, 4);            // tile pairs (256 batches each) per pass of a CTA
-    static constexpr int NB = T / gcd_k(T, 4);               // keystream blocks per thread per pass
-    static constexpr int PASS = PAIRS * 256;                 // batches per pass
-    static constexpr int DC = T / 2;                         // 16-byte chunks of a row holding draws
+    static constexpr int DC = (T + 1) / 2;                   // 16-byte chunks of a row holding draws (odd t: half of the last unused)
     static constexpr int SC = (K + 1) / 2;                   // ... holding secrets
     static constexpr int NKD = (DC + 1) / 2, NKS = (SC + 1) / 2;
     static constexpr int NK = NKD + NKS;                     // MMAs per tile (32 bytes of K each)
+    static constexpr int NMMA = (8 * N + 15) / 16 * 16;
+    // shared memory with `pairs` tile pairs (256 batches each) per pass: draws twice, secrets, two images, raw secrets
+    static constexpr uint32_t smem_for(int pairs) {
+        return 2 * (pairs * 2 * 16 * DC * 128 + 128) + (pairs * 2 * 16 * SC * 128 + 128) + 2 * (NMMA / 8 * 2 * NK * 128) +
+               pairs * 256 * K * 8;
+    }
+    // two pairs per pass give every thread whole keystream blocks when t is not a multiple of 4 -- where four CTAs
+    // still fit an SM with them (56960 bytes each after the per-CTA reserve); otherwise one pair, and the warps of a CTA
+    // share the pass's 32 t blocks unevenly
+    static constexpr int PAIRS = T % 4 != 0 && smem_for(2) <= 56960 ? 2 : 1;
+    static constexpr int PASS = PAIRS * 256;                 // batches per pass
+    static constexpr int NBLK = PASS * T / 8;                // keystream blocks per pass (8 draws each), a multiple of 32
+    static constexpr int NB = (NBLK + CTA2 - 1) / CTA2;      // ... per thread; odd t leaves the last round to warps 0 and 1
     // an odd chunk count lets the second chunk of the last K step alias the next 8-row group: B is 0 there
     static constexpr uint32_t SBO_D = DC * 128, SBO_S = SC * 128;
     static constexpr uint32_t D_TILE = 16 * SBO_D, S_TILE = 16 * SBO_S;
     static constexpr uint32_t D_BYTES = PAIRS * 2 * D_TILE + 128, S_BYTES = PAIRS * 2 * S_TILE + 128;
-    static constexpr int NMMA = (8 * N + 15) / 16 * 16;
     static constexpr uint32_t SBO_B = 2 * NK * 128;
     static constexpr uint32_t B_IMG = NMMA / 8 * SBO_B;      // one operand image; the kernel holds two (E, O)
     static constexpr uint32_t IN_BYTES = PASS * K * 8;       // the raw secrets of one pass
@@ -82,10 +93,15 @@ struct Shape2 {
     static constexpr int ACC_BUFS = 2 * ACC_COLS <= 128 ? 2 : 1;   // E and O side by side when four CTAs still fit
     static constexpr int TMEM_COLS = ACC_BUFS * ACC_COLS;
     static constexpr uint32_t IDESC = idesc_u8(NMMA);
+    static_assert(SMEM == smem_for(PAIRS), "smem_for restates SMEM");
+    // CTAs per SM that shared memory and TMEM allow: what the register allocation of the RTN instantiations is held to
+    static constexpr int RESIDENT = SMEM + 1152 > 227 * 1024 / 2 ? 1 : SMEM + 1152 > 227 * 1024 / 3 ? 2 : SMEM + 1152 > 227 * 1024 / 4 ? 3 : 4;
     static_assert(D_BYTES % 128 == 0 && S_BYTES % 128 == 0 && B_IMG % 16 == 0 && IN_BYTES % 16 == 0, "alignment");
     // the four BASELINE shapes fit four CTAs per SM (SMEM <= 56 KB); larger k of the run-time-share-count grid fit fewer
 };
 
+// (rotates as wide multiplies on the FMA pipe, 1 or 2 of the 4, cost +4 % / +19 % cycles: IMAD.WIDE holds the issue port
+// for ~4.8 cycles -- profiles/r01_pipes.md, profiles/r02_k2.md)
 #define SDA_QR2(a, b, c, d)                                     \
     a += b; d ^= a; d = __funnelshift_l(d, d, 16);              \
     c += d; b ^= c; b = __funnelshift_l(b, b, 12);              \
@@ -242,13 +258,44 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
     pre[0] = kr.pa.x; pre[1] = kr.pa.y; pre[2] = kr.pa.z; pre[3] = kr.pa.w;
     pre[4] = kr.pb.x; pre[5] = kr.pb.y; pre[6] = kr.pb.z; pre[7] = kr.pb.w;
     pre[8] = kr.pc.x; pre[9] = kr.pc.y; pre[10] = kr.pc.z; pre[11] = kr.pc.w;
-    const uint32_t blk0 = u * (uint32_t)(CTA2 * S::NB);           // the launcher keeps a participant below 2^32 blocks
+    const uint32_t blk0 = u * (uint32_t)S::NBLK;                  // the launcher keeps a participant below 2^32 blocks
+    // where 16-byte chunk c of batch beta (of the pass) lies
+    auto chunk_at = [&](uint32_t beta, uint32_t c) {
+        const uint32_t tile = (beta >> 8) * 2 + (beta & 1), row = (beta & 255) >> 1;
+        return sD + tile * S::D_TILE + (row >> 3) * S::SBO_D + c * LBO + (row & 7) * 16;
+    };
 #pragma unroll 1
     for (int nb = 0; nb < S::NB; nb++) {
         const uint32_t slot = nb * CTA2 + tid;                    // block of this pass, in stream order
+        if constexpr (S::NBLK % CTA2 != 0) {
+            if (slot >= (uint32_t)S::NBLK) break;                 // warp-uniform: NBLK is a multiple of 32
+        }
         uint32_t w[16];
         chacha_block2<ROUNDS>(k, pre, blk0 + slot, w);
         uint32_t suspect = 0;
+        if constexpr (S::TT % 2 != 0) {
+            // odd t: a block's 8 draws cross batch boundaries at odd positions -- one 8-byte store per draw
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint64_t x = reduce_draw2(w[2 * i], w[2 * i + 1], suspect);
+                const uint32_t g = slot * 8 + i, beta = g / S::TT, c = g % S::TT;
+                uint32_t xl, xh;
+                unpack(x, xl, xh);
+                *reinterpret_cast<uint2 *>(chunk_at(beta, c >> 1) + (c & 1) * 8) = make_uint2(xl, xh);
+            }
+        } else if constexpr (!(S::DC == 1 || S::DC == 2 || S::DC % 4 == 0)) {
+            // even t whose chunks per batch do not divide a block's four: every chunk placed on its own
+#pragma unroll
+            for (int cb = 0; cb < 4; cb++) {
+                const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1], suspect);
+                const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3], suspect);
+                const uint32_t gc = slot * 4 + cb;
+                uint32_t xal, xah, xbl, xbh;
+                unpack(xa, xal, xah);
+                unpack(xb, xbl, xbh);
+                *reinterpret_cast<uint4 *>(chunk_at(gc / S::DC, gc % S::DC)) = make_uint4(xal, xah, xbl, xbh);
+            }
+        } else {
         // the block's four chunks: chunk 0 goes to `dst`, the others to compile-time offsets from it
         const uint32_t gc0 = slot * 4;
         const uint32_t beta0 = gc0 / S::DC, c0 = gc0 % S::DC;
@@ -261,7 +308,6 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
             // DC = 1: batches beta0 .. beta0 + 3 (beta0 a multiple of 4): tiles E, O, E, O, rows row0, row0, row0 + 1, row0 + 1
             // DC = 2: batches beta0, beta0 + 1 (beta0 even): tiles E, E, O, O, chunks 0, 1, 0, 1 of row row0
             // DC % 4 == 0: one batch, chunks c0 .. c0 + 3
-            static_assert(S::DC == 1 || S::DC == 2 || S::DC % 4 == 0, "draw chunks per batch");
             const uint32_t delta = S::DC == 1 ? (cb & 1) * S::D_TILE + (cb >> 1) * 16
                                  : S::DC == 2 ? (cb >> 1) * S::D_TILE + (cb & 1) * LBO
                                               : cb * LBO;
@@ -269,6 +315,7 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
             unpack(xa, xal, xah);
             unpack(xb, xbl, xbh);
             *reinterpret_cast<uint4 *>(dst + delta) = make_uint4(xal, xah, xbl, xbh);
+        }
         }
         if (suspect >= LOW29) {
             bool bad = false;
@@ -342,7 +389,7 @@ __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint
 // for): shares are folded and stored one at a time (tcgen05.ld.x8 per share and accumulator, the next share's loads in
 // flight under the current fold) instead of through N-wide unrolled register arrays.  packed_tc2n.cu instantiates it.
 template <int K, int T, int N, int ROUNDS, bool RTN = false>
-__global__ void __launch_bounds__(CTA2, 1)
+__global__ void __launch_bounds__(CTA2, RTN ? Shape2<K, T, N>::RESIDENT : 1)
 packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
                         uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
                         const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,
@@ -350,11 +397,13 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
     typedef Shape2<K, T, N> S;
     static_assert(!RTN || S::ACC_BUFS == 2, "the run-time share count needs both accumulators of a pair at once");
     const uint32_t nsh = RTN ? n_rt : (uint32_t)N;         // shares per batch
+    // RTN: the shares go through the accumulators in groups of N (one pair of operand images per group)
+    const uint32_t ngroups = RTN ? (n_rt + N - 1) / N : 1u;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sD = smem;                                    // 2 x (PAIRS x {E, O} tiles x 128 rows x draws)
     uint8_t *sS = smem + 2 * S::D_BYTES;                   // PAIRS x {E, O} tiles x 128 rows x secrets
     uint8_t *sB = sS + S::S_BYTES;                         // the constant operand, E image then O image
-    int64_t *sIn = reinterpret_cast<int64_t *>(sB + 2 * S::B_IMG);   // the coming pass's raw secrets
+    int64_t *sIn = reinterpret_cast<int64_t *>(sB + ngroups * (2 * S::B_IMG));   // the coming pass's raw secrets
     __shared__ __align__(8) uint64_t mbar[3];              // [0] full (MMAs done), [1] drained (TMEM read out), [2] secrets landed
     __shared__ uint32_t tmem_base;
 
@@ -373,7 +422,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[2])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (uint32_t i = tid; i < 2 * S::B_IMG / 16; i += CTA2) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
+    for (uint32_t i = tid; i < ngroups * (2 * S::B_IMG / 16); i += CTA2) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -488,13 +537,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
             }
             const bool fast_store = all_live && vec_ok != 0;                 // uniform: one 16-byte store per share row
             if constexpr (RTN) {
-                mbar_wait(full_bar, parity);
-                parity ^= 1;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t ta = my_taddr, tb = my_taddr + S::ACC_COLS;
-                uint32_t e0[8], o0[8], e1[8], o1[8];
-                tmem_ld8(ta, e0);
-                tmem_ld8(tb, o0);
                 char *ptr = optr;
                 auto put = [&](const uint32_t (&de)[8], const uint32_t (&dd)[8]) {
                     const uint64_t ra = compose2<S::W5>(de, two16), rb = compose2<S::W5>(dd, two16);
@@ -506,37 +549,51 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     ptr += row_bytes;
                 };
 #pragma unroll 1
-                for (uint32_t j = 0; j < nsh; j += 2) {
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (j + 1 < nsh) {
-                        tmem_ld8(ta + 8 * (j + 1), e1);
-                        tmem_ld8(tb + 8 * (j + 1), o1);
-                    }
-                    put(e0, o0);
-                    if (j + 1 < nsh) {
+                for (uint32_t g = 0; g < ngroups; g++) {
+                    const uint32_t nsg = min((uint32_t)N, nsh - g * N);          // shares of this group
+                    mbar_wait(full_bar, parity);
+                    parity ^= 1;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t e0[8], o0[8], e1[8], o1[8];
+                    tmem_ld8(ta, e0);
+                    tmem_ld8(tb, o0);
+#pragma unroll 1
+                    for (uint32_t j = 0; j < nsg; j += 2) {
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (j + 2 < nsh) {
-                            tmem_ld8(ta + 8 * (j + 2), e0);
-                            tmem_ld8(tb + 8 * (j + 2), o0);
+                        if (j + 1 < nsg) {
+                            tmem_ld8(ta + 8 * (j + 1), e1);
+                            tmem_ld8(tb + 8 * (j + 1), o1);
                         }
-                        put(e1, o1);
-                    }
-                }
-                if (q + 1 < S::PAIRS) {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
-                    if (warp == 0) {
-                        mbar_wait(drained_bar, dparity);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        if (elect_one()) {
-                            issue_tile2<S>(taddr, d_cur + (2 * q + 2) * S::D_TILE, s_base + (2 * q + 2) * S::S_TILE, b_base);
-                            issue_tile2<S>(taddr + S::ACC_COLS, d_cur + (2 * q + 3) * S::D_TILE, s_base + (2 * q + 3) * S::S_TILE,
-                                           b_base + S::B_IMG);
-                            commit2(full_bar);
+                        put(e0, o0);
+                        if (j + 1 < nsg) {
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                            if (j + 2 < nsg) {
+                                tmem_ld8(ta + 8 * (j + 2), e0);
+                                tmem_ld8(tb + 8 * (j + 2), o0);
+                            }
+                            put(e1, o1);
                         }
-                        __syncwarp();
                     }
-                    dparity ^= 1;
+                    // the accumulators are read out: the next group of this pair, or the first group of the next pair
+                    const bool next_group = g + 1 < ngroups;
+                    if (next_group || q + 1 < S::PAIRS) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(drained_bar) : "memory");
+                        if (warp == 0) {
+                            mbar_wait(drained_bar, dparity);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (elect_one()) {
+                                const uint32_t qn = next_group ? 2 * q : 2 * q + 2;
+                                const uint32_t bn = b_base + (next_group ? g + 1 : 0u) * (2 * S::B_IMG);
+                                issue_tile2<S>(taddr, d_cur + qn * S::D_TILE, s_base + qn * S::S_TILE, bn);
+                                issue_tile2<S>(taddr + S::ACC_COLS, d_cur + (qn + 1) * S::D_TILE, s_base + (qn + 1) * S::S_TILE,
+                                               bn + S::B_IMG);
+                                commit2(full_bar);
+                            }
+                            __syncwarp();
+                        }
+                        dparity ^= 1;
+                    }
                 }
                 optr += 256 * 8;
             } else if constexpr (S::ACC_BUFS == 2) {
@@ -675,11 +732,16 @@ cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size
     if ((unit_begin + units_per_p) >> 31 || units_total >> 31 || P >> 31) return cudaErrorInvalidValue;
     auto kern = packed_share_tc2_kernel<K, T, N, ROUNDS, RTN>;
     // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh)
-    const size_t smem = smem_capping_residency(S::SMEM, 512 / S::TMEM_COLS);
+    // RTN: one more pair of operand images per further group of N shares
+    const size_t n_groups = RTN ? ((size_t)n_rt + N - 1) / N : 1;
+    const size_t smem = smem_capping_residency(S::SMEM + (n_groups - 1) * (2 * S::B_IMG), 512 / S::TMEM_COLS);
     static KernelSetup setup;
     int regs = 0;
     size_t static_smem = 0;
-    const cudaError_t se = setup_kernel(setup, kern, smem, &regs, &static_smem);
+    // the attribute is set once per device: for RTN, to what the largest share count (SDA_TC2_MAX_GROUPS groups) needs
+    const size_t smem_limit = RTN ? smem_capping_residency(S::SMEM + (SDA_TC2_MAX_GROUPS - 1) * (2 * S::B_IMG), 512 / S::TMEM_COLS) : smem;
+    if (n_groups > SDA_TC2_MAX_GROUPS || smem_limit > 227u * 1024u) return cudaErrorInvalidValue;
+    const cudaError_t se = setup_kernel(setup, kern, smem_limit, &regs, &static_smem);
     if (se != cudaSuccess) return se;
     const int per_sm = resident_ctas(regs, CTA2, smem, static_smem, S::TMEM_COLS);
     size_t grid = (size_t)lc.sm_count * per_sm;

@@ -55,10 +55,12 @@ template <int TMEM_COLS>
 __global__ void __launch_bounds__(CTA)
 reveal_tc_kernel(const int64_t *__restrict__ shares, size_t ld, size_t nbatches, size_t dimension, int k, int m, int chunks,
                  int nk, uint32_t sbo_a, uint32_t a_bytes, uint32_t sbo_b, uint32_t b_bytes, uint32_t idesc,
-                 const uint4 *__restrict__ b_image, int64_t *__restrict__ out, uint32_t two16) {
+                 const uint4 *__restrict__ b_image, int64_t *__restrict__ out, uint32_t two16, int bulk_ok) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *sA = smem;
     uint8_t *sB = smem + ((a_bytes + 127) & ~127u);
+    // a tile's 128 k secrets are contiguous in the output: composed into shared memory, stored by one bulk copy
+    uint64_t *sOut = reinterpret_cast<uint64_t *>(sB + ((b_bytes + 127) & ~127u));
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -127,6 +129,8 @@ reveal_tc_kernel(const int64_t *__restrict__ shares, size_t ld, size_t nbatches,
                 stage_chunk(c, v0, v1);
             }
         }
+        // the previous tile's bulk store has read its staging buffer before anyone passes the barrier below
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -142,16 +146,29 @@ reveal_tc_kernel(const int64_t *__restrict__ shares, size_t ld, size_t nbatches,
         parity ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const size_t o0 = b * (size_t)k;
+        const size_t tile_first = tile * (size_t)(CTA * k);
+        const bool by_bulk = bulk_ok != 0 && tile_first + (size_t)(CTA * k) <= dimension;     // a whole tile inside the vector
+        uint32_t d[8], dn[8];
+        tmem_ld8(my_taddr, d);
         for (int e = 0; e < k; e++) {
-            uint32_t d[8];
-            tmem_ld8(my_taddr + 8 * e, d);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (e + 1 < k) tmem_ld8(my_taddr + 8 * (e + 1), dn);      // the next secret's limbs, in flight under this compose
             const uint64_t r = compose(d, two16);
-            if (b < nbatches && o0 + e < dimension) out[o0 + e] = (int64_t)r;      // batched.rs:94 truncate
+            if (by_bulk) sOut[tid * k + e] = r;
+            else if (b < nbatches && o0 + e < dimension) out[o0 + e] = (int64_t)r;      // batched.rs:94 truncate
+#pragma unroll
+            for (int i = 0; i < 8; i++) d[i] = dn[i];
         }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();          // TMEM and the rows are free for the next tile
+        __syncthreads();          // TMEM and the rows are free for the next tile; the staged secrets are complete
+        if (by_bulk && tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(out + tile_first), "r"(smem_u32(sOut)), "r"((uint32_t)(CTA * k * 8)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // shared memory outlives the last store
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(TMEM_COLS) : "memory");
 }
@@ -162,7 +179,9 @@ cudaError_t launch(const LaunchCtx &lc, const RevealShape &s, const int64_t *sha
     auto kern = reveal_tc_kernel<TMEM_COLS>;
     // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh): this kernel needs few registers
     // and little shared memory, so without the floor 12 CTAs land on an SM that has columns for 512 / TMEM_COLS
-    const size_t smem = smem_capping_residency(((s.a_bytes + 127) & ~127u) + s.b_bytes, 512 / TMEM_COLS);
+    const size_t smem = smem_capping_residency(((s.a_bytes + 127) & ~127u) + ((s.b_bytes + 127) & ~127u) + (size_t)CTA * s.k * 8,
+                                               512 / TMEM_COLS);
+    const int bulk_ok = reinterpret_cast<uintptr_t>(out) % 16 == 0;      // bulk stores need 16-byte aligned destinations
     static KernelSetup setup;                              // one per TMEM size (this function is a template)
     int regs = 0;
     size_t static_smem = 0;
@@ -173,7 +192,7 @@ cudaError_t launch(const LaunchCtx &lc, const RevealShape &s, const int64_t *sha
     const size_t grid = std::min<size_t>(tiles, (size_t)lc.sm_count * per_sm);
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(shares, ld, nbatches, dimension, s.k, s.m, s.chunks, s.nk, s.sbo_a,
                                                    s.a_bytes, s.sbo_b, s.b_bytes, idesc_u8(s.n_mma),
-                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u);
+                                                   reinterpret_cast<const uint4 *>(d_b_image), out, 65536u, bulk_ok);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }

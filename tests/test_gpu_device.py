@@ -38,11 +38,12 @@ def test_synth_fill_matches_oracle(ctx, oracle, torch_cuda):
             assert np.array_equal(host(out), oracle.synth_fill(3, m, start, count)), (m, start, count)
 
 
-@pytest.mark.parametrize("path", [1, 2], ids=["cuda_cores", "tensor_cores"])
+@pytest.mark.parametrize("path", [1, 2, 3, 4], ids=["cuda_cores", "tensor_cores", "tensor_cores_v1", "tensor_cores_any_shape"])
 @pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
 def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
-    """both Mersenne-61 share-gen kernels (IMAD.WIDE limbs / tcgen05 byte-limb GEMM) against the oracle:
-    several participants, dims that end inside a tile, negative and out-of-range secrets"""
+    """every Mersenne-61 share-gen kernel a BASELINE shape can be sent to (IMAD.WIDE limbs; tcgen05 byte-limb GEMM: paired
+    tiles, first generation, share count at run time) against the oracle: several participants, dims that end inside a
+    tile, negative and out-of-range secrets"""
     t = torch_cuda
     s = mk()
     k = s.input_size()
@@ -59,7 +60,8 @@ def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
             d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
             ctx.share_generate_dev(s, dev(t, secrets), dim, P, dim, seeds, d_out)
             ctx.synchronize()
-            assert ("tcgen05" in ctx.last_kernel()) == (path == 2)
+            assert ("tcgen05" in ctx.last_kernel()) == (path >= 2)
+            assert ("at run time" in ctx.last_kernel()) == (path == 4) and ("paired" in ctx.last_kernel()) == (path in (2, 4))
             got = host(d_out)
             for pi in range(P):
                 exp = util.oracle_generate(oracle, s, secrets[pi], seeds[32 * pi:32 * pi + 32], matrix=True)
@@ -68,11 +70,13 @@ def test_packed_kernels_agree_with_oracle(ctx, oracle, torch_cuda, mk, path):
         ctx.set_packed_path(0)
 
 
-@pytest.mark.parametrize("shape", [(4, 2, 6), (2, 4, 8), (8, 2, 3), (1, 4, 5), (7, 4, 7), (3, 2, 6)])
+@pytest.mark.parametrize("shape", [(4, 2, 6), (2, 4, 8), (8, 2, 3), (1, 4, 5), (7, 4, 7), (3, 2, 6),
+                                   (3, 3, 7), (5, 1, 12), (2, 6, 9), (7, 5, 16), (8, 8, 32), (1, 7, 3), (4, 3, 20), (1, 1, 2)])
 @pytest.mark.parametrize("offset,ld_pad", [(0, 0), (1, 1)])
 def test_paired_tile_kernel_with_run_time_share_count(ctx, oracle, torch_cuda, shape, offset, ld_pad):
-    """packed_tc2n.cu: (k, t) templated, n <= 8 at run time, over 2^61-1: several participants, aligned (bulk copy, 16-byte
-    stores) and unaligned sources, vectors ending inside a pass, negative secrets -- every share against the oracle"""
+    """packed_tc2n.cu: (k, t) templated (k, t <= 8, odd t included), n <= 32 at run time in groups of 8, over 2^61-1:
+    several participants, aligned (bulk copy, 16-byte stores) and unaligned sources, vectors ending inside a pass,
+    negative secrets -- every share against the oracle"""
     t = torch_cuda
     k, tt, n = shape
     s = util.packed_scheme(P61, k, tt, n, oracle)
@@ -97,7 +101,7 @@ def test_paired_tile_kernel_with_run_time_share_count(ctx, oracle, torch_cuda, s
             assert np.array_equal(got[pi], util.canon(oracle, P61, exp)), (shape, P, dim, pi)
 
 
-@pytest.mark.parametrize("shape", [(2, 3, 6), (7, 5, 16), (1, 1, 2), (4, 1, 9), (9, 7, 32)])
+@pytest.mark.parametrize("shape", [(2, 3, 6), (7, 5, 16), (1, 1, 2), (4, 1, 9), (9, 7, 32), (12, 2, 20), (2, 10, 13)])
 @pytest.mark.parametrize("p", [P61, params.P61_GENERIC])
 def test_runtime_shaped_kernel_many_participants(ctx, oracle, torch_cuda, shape, p):
     """packed_tcg.cu on device buffers: several participants, vectors spanning many passes and ending inside one,
@@ -118,7 +122,8 @@ def test_runtime_shaped_kernel_many_participants(ctx, oracle, torch_cuda, shape,
         d_out = t.empty((P, n, B), dtype=t.int64, device="cuda")
         ctx.share_generate_dev(s, dev(t, secrets), ld, P, dim, seeds, d_out)
         ctx.synchronize()
-        assert "run-time shape" in ctx.last_kernel() and "tcgen05" in ctx.last_kernel()
+        paired = p == P61 and k <= 8 and tt <= 8       # those take packed_tc2n.cu (tested above)
+        assert ("at run time" if paired else "run-time shape") in ctx.last_kernel() and "tcgen05" in ctx.last_kernel()
         got = host(d_out)
         for pi in range(P):
             exp = util.oracle_generate(oracle, s, secrets[pi, :dim], seeds[32 * pi:32 * pi + 32], matrix=True)
@@ -322,6 +327,32 @@ def test_config3_full_size(ctx, oracle, torch_cuda):
     ctx.synchronize()
     assert t.equal(d_rec, d_tot)
     assert int(d_sh.min()) >= 0 and int(d_sh.max()) < P61
+
+
+@pytest.mark.parametrize("mk", [params.config3, params.config4, params.config5], ids=["cfg3", "cfg4", "cfg5"])
+@pytest.mark.parametrize("out_offset", [0, 1])
+def test_reveal_many_tiles_any_alignment(ctx, oracle, torch_cuda, mk, out_offset):
+    """reveal_tc.cu on device buffers: more tiles than resident CTAs (every CTA loops), a vector that ends inside a tile and
+    inside a batch, an output that is / is not 16-byte aligned (bulk stores / per-thread stores), shares that are negative
+    representatives, a subset of the clerks -- against the oracle's reconstruction"""
+    t = torch_cuda
+    s = mk()
+    c = s.c
+    p, k, n, need = c.modulus, c.secret_count, c.share_count, c.secret_count + c.privacy_threshold
+    so = util.to_oracle_sharing(oracle, s)
+    rng = np.random.default_rng(k + out_offset)
+    for dim in (128 * k * 2500 + 128 * k - 1, 128 * k * 3, 128 * k * 2 + k + 1):
+        B = s.batches(dim)
+        idx = sorted(rng.permutation(n)[:need + (need < n)].tolist())
+        shares = rng.integers(0, p, size=(len(idx), B), dtype=np.int64)
+        exp = util.canon(oracle, p, oracle.secret_reconstruct(so, dim, idx, shares))
+        shares[:, ::5] -= p                                   # another representative of the same residue
+        d_out = t.full((dim + 2,), -1, dtype=t.int64, device="cuda")
+        ctx.secret_reconstruct_dev(s, dim, idx, dev(t, shares), B, len(idx), B, d_out[out_offset:])
+        ctx.synchronize()
+        got = host(d_out)
+        assert np.array_equal(got[out_offset:out_offset + dim], exp), (dim, idx)
+        assert (got[:out_offset] == -1).all() and (got[out_offset + dim:] == -1).all()      # nothing beyond the vector
 
 
 def test_config2_full_size(ctx, oracle, torch_cuda):

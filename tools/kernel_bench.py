@@ -109,7 +109,7 @@ def main():
             ctx.synth_fill_dev(4, P61, 0, P * dim, sec)
             sh = empty(P, n, B)
             sd = seeds(name, P)
-            for path, label in ((2, "tensor cores"), (1, "CUDA cores")):
+            for path, label in ((2, "tensor cores"), (4, "tensor cores, share count at run time"), (1, "CUDA cores")):
                 ctx.set_packed_path(path)
                 timeit(f"packed_share {name} [{P}][10M] ({label})",
                        lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n * B) * 8,
@@ -148,7 +148,7 @@ def main():
             print(json.dumps({"kernel": "packed_share generic prime", "skipped": str(e)}), flush=True)
 
         # ---- shapes without a templated kernel: the run-time-shaped tcgen05 kernel (packed_tcg.cu) ---------------------
-        for k_, t_, n_ in ((3, 2, 6), (3, 2, 4), (5, 4, 8), (4, 2, 8), (3, 3, 7), (5, 4, 10), (8, 8, 20)):
+        for k_, t_, n_ in ((3, 2, 6), (3, 2, 4), (5, 4, 8), (4, 2, 8), (3, 3, 7), (5, 4, 10), (8, 8, 20), (2, 5, 9), (8, 1, 12), (12, 3, 20)):
             s = params.LinearSecretSharingScheme.PackedShamir(k_, n_, t_, P61, params.ROOT_ORDER_31, params.ROOT_ORDER_41)
             P, dim = 64, 10_000_000
             B = s.batches(dim)
