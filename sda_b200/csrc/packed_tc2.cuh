@@ -40,23 +40,6 @@ constexpr int SDA_TC2_MAX_GROUPS = 4;  // run-time share count: up to 4 groups o
 
 constexpr int gcd_k(int a, int b) { return b == 0 ? a : gcd_k(b, a % b); }
 
-// width of limb 5 of the constant operand (see compose2): the widest for which e2 = d4 + 256 d5 stays below 2^29
-// when a limb sum has 8 (k + t) terms of at most 255 * (2^w - 1)
-constexpr int w5_for(int kt) {
-    for (int w5 = 8; w5 >= 5; w5--)
-        if ((long long)8 * kt * 255 * (255 + ((1ll << w5) - 1) * 256) < (1ll << 29)) return w5;
-    return 0;
-}
-
-struct LimbPlan {
-    int w[8], pos[8];
-};
-inline LimbPlan limb_plan(int kt) {
-    const int w5 = w5_for(kt);
-    LimbPlan lp{{8, 8, 8, 8, 8, w5, 8, 13 - w5}, {0, 8, 16, 24, 32, 40, 40 + w5, 48 + w5}};
-    return lp;
-}
-
 template <int K, int T, int N>
 struct Shape2 {
     static_assert(T >= 1, "at least one draw per batch");
@@ -173,43 +156,6 @@ __device__ __forceinline__ uint64_t reduce_draw2(uint32_t w0, uint32_t w1, uint3
     return pack(w1, w0) + (uint64_t)h;
 }
 
-// canonical  sum_s d[s] 2^{pos[s]}  mod p  for the limb sums of one share (limb plan of k + t: positions
-// 0,8,16,24,32,40,40+W5,48+W5).  e0..e3 are 32-bit; X = e0 + e1 2^16 + e2 2^32 < 2^61 + 2^48 is one wide multiply
-// whose addend is the register pair (e0, e2); e3 2^{40+W5} == (e3 mod 2^{21-W5}) 2^{40+W5} + (e3 >> (21-W5)) because
-// 2^61 == 1; t = value + 1 lies in [1, 2^62) and the last four instructions are packed_tc.cu's.
-#ifndef SDA_TC2_XWIDE
-#define SDA_TC2_XWIDE 0      // 1: X by IMAD.WIDE with a run-time multiplier (one FMA-pipe instruction) instead of LEA + LEA.HI.X
-#endif
-#ifndef SDA_TC2_FINAL_X
-#define SDA_TC2_FINAL_X 1    // 1: the final 64-bit add takes its high addend from a register (IMAD.X) instead of a sign extension
-#endif
-template <int W5>
-__device__ __forceinline__ uint64_t compose2(const uint32_t (&d)[8], uint32_t two16) {
-    const uint32_t e0 = d[0] + (d[1] << 8), e1 = d[2] + (d[3] << 8);
-    const uint32_t e2 = d[4] + (d[5] << 8), e3 = d[6] + (d[7] << 8);
-    uint64_t x;
-#if SDA_TC2_XWIDE
-    // two16 == 65536 is a kernel parameter so that ptxas keeps the multiply (it turns a literal into two shifts-and-adds)
-    asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, %4, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1), "r"(two16));
-#else
-    asm("{\n\t.reg .u64 a;\n\tmov.b64 a, {%1, %2};\n\tmad.wide.u32 %0, %3, 65536, a;\n\t}" : "=l"(x) : "r"(e0), "r"(e2), "r"(e1));
-#endif
-    constexpr uint32_t SH3 = 8 + W5;                                  // position of e3 inside the high word
-    const uint32_t m3 = (e3 << SH3) & (LOW29 & ~((1u << SH3) - 1u));
-    const uint32_t s3 = (e3 >> (21 - W5)) + 1u;                       // + 1: t == value + 1
-    const uint64_t t = x + pack(s3, m3);
-    uint32_t t_lo, t_hi;
-    unpack(t, t_lo, t_hi);
-    const uint32_t qm1 = (t_hi >> 29) - 1u;                           // floor((t - 1) / p) - 1 in {-1, 0} as two's complement
-    uint32_t r_lo, r_hi;
-#if SDA_TC2_FINAL_X
-    unpack(t + pack(qm1, qm1), r_lo, r_hi);                           // the 64-bit value -1 or 0: both words equal qm1
-#else
-    unpack(t + (uint64_t)(int64_t)(int32_t)qm1, r_lo, r_hi);
-#endif
-    return pack(r_lo, r_hi & LOW29);
-}
-
 // one elected lane of a converged warp: the NK MMAs of a 128-row tile into the accumulator at `taddr`
 template <class S>
 __device__ __forceinline__ void issue_tile2(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_img) {
@@ -221,15 +167,6 @@ __device__ __forceinline__ void issue_tile2(uint32_t taddr, uint32_t d_tile, uin
     for (int kk = 0; kk < S::NKS; kk++)
         umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
 }
-__device__ __forceinline__ void commit2(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
 // the keystream of one pass: NB blocks per thread, every draw reduced and scattered into the row it belongs to.
 // Chunk gc of the pass (16 bytes = two draws, stream order) belongs to batch gc / DC of the pass; batch beta sits in
 // tile pair beta / 256, tile E or O by its parity, row (beta % 256) / 2.

@@ -294,6 +294,28 @@ def test_packed_reconstruct(ctx, oracle, name, mk):
         ctx.secret_reconstruct(s, 5 * k, [(i, [0]) for i in range(n)])
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 3), (2, 3, 6), (4, 3, 10), (7, 5, 16), (8, 8, 20), (15, 1, 17), (1, 15, 32), (3, 3, 7),
+                                   (6, 7, 14), (5, 2, 9), (1, 2, 3), (8, 1, 9), (2, 1, 4), (10, 1, 12)])
+def test_packed_reconstruct_generic_shapes(ctx, oracle, shape):
+    """reveal for any (k, t, n) over 2^61-1: every clerk-subset size from k + t to n (up to 16 present clerks on the tcgen05
+    kernel -- every chunk count and both parities of m' -- more on the CUDA-core one), vectors that end inside a tile and
+    inside a batch, against the oracle's Newton interpolation"""
+    k, t, n = shape
+    try:
+        s = util.packed_scheme(P61, k, t, n, oracle)
+    except StopIteration:
+        pytest.skip("no suitable prime orders in p-1")
+    rng = np.random.default_rng(100 * k + n)
+    need = k + t
+    for dim in (1, k + 1, 128 * k * 3 - 1, 128 * k * 19 + 2):
+        secrets = util.rand_secrets(rng, dim, P61)
+        shares = util.oracle_generate(oracle, s, secrets, util.seed_bytes(f"rec/{shape}/{dim}"), matrix=True)
+        for m in sorted({need, min(need + 1, n), min(16, n), n}):
+            idx = sorted(rng.permutation(n)[:m].tolist())
+            got = ctx.secret_reconstruct(s, dim, [(i, shares[i]) for i in idx])
+            assert np.array_equal(got, secrets), (shape, dim, idx)
+
+
 # ---- masking ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("modulus", [433, P61, PGEN, M_REJECT, 1])
 def test_full_mask_roundtrip_and_parity(ctx, oracle, modulus):

@@ -16,4 +16,12 @@ timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pyte
   > gpurun_out/sanitize_memcheck_r02.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_r02.log
 timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
   -k "(runtime_shaped and shape0 and 2305843009213693951) or (packed_kernels and cfg3 and tensor)" > gpurun_out/sanitize_racecheck_r02.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_r02.log
+# the paired-tile kernel with the share count at run time (even and odd t, two share groups), the reveal kernel with bulk
+# stores (aligned and unaligned outputs), the single-launch varint codec
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py tests/test_gpu_codec.py -q -m gpu \
+  -k "(run_time_share_count and (shape0 or shape6 or shape9)) or (reveal_many_tiles and cfg4) or varint" \
+  > gpurun_out/sanitize_memcheck_r02b.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_r02b.log
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py tests/test_gpu_codec.py -q -m gpu \
+  -k "(run_time_share_count and shape6 and 0-0) or (reveal_many_tiles and cfg3 and 0) or varint_known or varint_encode_decode" \
+  > gpurun_out/sanitize_racecheck_r02b.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_r02b.log
 (echo "compute-sanitizer on a B200 (tools/gpu_sanitize.sh), round 2"; for f in gpurun_out/sanitize_*.log; do echo "== $(basename $f)"; grep -v "^$" $f | tail -6; done) > gpurun_out/r02_sanitizer.txt
