@@ -147,18 +147,27 @@ def main():
         except Exception as e:                       # no suitable orders: skip the line
             print(json.dumps({"kernel": "packed_share generic prime", "skipped": str(e)}), flush=True)
 
-        # ---- shapes without a templated kernel: the run-time-shaped tcgen05 kernel (packed_tcg.cu) ---------------------
-        for k_, t_, n_ in ((3, 2, 6), (3, 2, 4), (5, 4, 8), (4, 2, 8), (3, 3, 7), (5, 4, 10), (8, 8, 20), (2, 5, 9), (8, 1, 12), (12, 3, 20)):
+        # ---- shapes without a fully templated kernel: the paired-tile kernel with the share count at run time
+        #      (packed_tc2n.cu), and with 12 rounds the run-time-shaped kernel (packed_tcg.cu) ---------------------------
+        for k_, t_, n_, rounds in ((3, 2, 6, 20), (3, 2, 4, 20), (5, 4, 8, 20), (4, 2, 8, 20), (3, 3, 7, 20), (5, 4, 10, 20),
+                                   (8, 8, 20, 20), (2, 5, 9, 20), (8, 1, 12, 20), (12, 3, 20, 20), (2, 10, 13, 20),
+                                   (3, 2, 6, 12), (8, 8, 20, 12)):
+            if args.rounds != 20:              # a sweep at another round count: the 20-round lines only, at that count
+                if rounds != 20:
+                    continue
+                rounds = args.rounds
             s = params.LinearSecretSharingScheme.PackedShamir(k_, n_, t_, P61, params.ROOT_ORDER_31, params.ROOT_ORDER_41)
             P, dim = 64, 10_000_000
+            ctx.set_rng_rounds(rounds)
             B = s.batches(dim)
             sec = empty(P, dim)
             ctx.synth_fill_dev(10, P61, 0, P * dim, sec)
             sh = empty(P, n_, B)
             sd = seeds(f"rt{k_}{t_}{n_}", P)
-            timeit(f"packed_share k={k_} t={t_} n={n_} [{P}][10M] (no fully templated kernel)",
+            timeit(f"packed_share k={k_} t={t_} n={n_} [{P}][10M] (no fully templated kernel{'' if rounds == args.rounds else f', ChaCha{rounds}'})",
                    lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n_ * B) * 8,
                    f"8(1+n/k) = {8 * (1 + n_ / k_):.2f} B per secret")
+            ctx.set_rng_rounds(args.rounds)
             del sec, sh
             torch.cuda.empty_cache()
         # ---- additive split with a share count beyond the unrolled kernels (n = 9) ---------------------------------------
