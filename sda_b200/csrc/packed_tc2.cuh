@@ -122,7 +122,12 @@ __device__ __forceinline__ void chacha_block2(const uint32_t (&k)[8], const uint
     uint32_t x2 = pre[4], x6 = pre[5], x10 = pre[6], x14 = pre[7];
     uint32_t x3 = pre[8], x7 = pre[9], x11 = pre[10], x15 = pre[11];
     SDA_QR2(x0, x4, x8, x12)                   // the one column of round 1 that sees the counter
-#pragma unroll 3
+#ifndef SDA_TC2_UNROLL
+#define SDA_TC2_UNROLL 9     // full unrolling of the 9 double rounds: -2.2 % cycles against 3 (no loop-carried register moves)
+#endif
+#define SDA_TC2_PRAGMA_(x) _Pragma(#x)
+#define SDA_TC2_PRAGMA(x) SDA_TC2_PRAGMA_(x)
+    SDA_TC2_PRAGMA(unroll SDA_TC2_UNROLL)
     for (int i = 0; i < ROUNDS / 2 - 1; i++) {  // diagonal round, then the next column round
         SDA_QR2(x0, x5, x10, x15)
         SDA_QR2(x1, x6, x11, x12)
@@ -149,11 +154,27 @@ __device__ __forceinline__ void chacha_block2(const uint32_t (&k)[8], const uint
 // v mod 2^61 >= 2^61 - 32 (a rejected word, a wrap-around of the reduction, or the overflow of this very sum).  The
 // necessary condition "bits 32..60 all ones" (2^-29 per draw) is accumulated as the running maximum of the masked
 // high words (one three-input VIMNMX per two draws), and the caller settles `suspect >= 2^29 - 1` exactly.
-__device__ __forceinline__ uint64_t reduce_draw2(uint32_t w0, uint32_t w1, uint32_t &suspect) {
+__device__ __forceinline__ uint64_t reduce_draw2(uint32_t w0, uint32_t w1) {
     uint32_t h;
     asm("shr.u32 %0, %1, 29;" : "=r"(h) : "r"(w0));
-    suspect = max(suspect, w0 & LOW29);
     return pack(w1, w0) + (uint64_t)h;
+}
+// the running maximum over a block's 8 draws.  SDA_TC2_SUSPECT_PAIRS: two draws share one masked word -- "the OR of
+// their high words has bits 0..28 all ones" is still necessary for either of them, costs one LOP3 per pair instead of
+// one per draw, and is true by chance for 2^-12 of the pairs (the exact test that follows then finds nothing).
+#ifndef SDA_TC2_SUSPECT_PAIRS
+#define SDA_TC2_SUSPECT_PAIRS 1
+#endif
+__device__ __forceinline__ uint32_t suspect_of_block(const uint32_t (&w)[16]) {
+    uint32_t suspect = 0;
+#if SDA_TC2_SUSPECT_PAIRS
+#pragma unroll
+    for (int d = 0; d < 8; d += 2) suspect = max(suspect, (w[2 * d] | w[2 * d + 2]) & LOW29);
+#else
+#pragma unroll
+    for (int d = 0; d < 8; d++) suspect = max(suspect, w[2 * d] & LOW29);
+#endif
+    return suspect;
 }
 
 // one elected lane of a converged warp: the NK MMAs of a 128-row tile into the accumulator at `taddr`
@@ -209,12 +230,12 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
         }
         uint32_t w[16];
         chacha_block2<ROUNDS>(k, pre, blk0 + slot, w);
-        uint32_t suspect = 0;
+        const uint32_t suspect = suspect_of_block(w);
         if constexpr (S::TT % 2 != 0) {
             // odd t: a block's 8 draws cross batch boundaries at odd positions -- one 8-byte store per draw
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const uint64_t x = reduce_draw2(w[2 * i], w[2 * i + 1], suspect);
+                const uint64_t x = reduce_draw2(w[2 * i], w[2 * i + 1]);
                 const uint32_t g = slot * 8 + i, beta = g / S::TT, c = g % S::TT;
                 uint32_t xl, xh;
                 unpack(x, xl, xh);
@@ -224,8 +245,8 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
             // even t whose chunks per batch do not divide a block's four: every chunk placed on its own
 #pragma unroll
             for (int cb = 0; cb < 4; cb++) {
-                const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1], suspect);
-                const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3], suspect);
+                const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1]);
+                const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3]);
                 const uint32_t gc = slot * 4 + cb;
                 uint32_t xal, xah, xbl, xbh;
                 unpack(xa, xal, xah);
@@ -240,8 +261,8 @@ __device__ __forceinline__ void stage_draws2(const KeyRegs &kr, uint32_t u, int 
         uint8_t *dst = sD + tile0 * S::D_TILE + (row0 >> 3) * S::SBO_D + c0 * LBO + (row0 & 7) * 16;
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {                          // 4 chunks of 2 draws
-            const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1], suspect);
-            const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3], suspect);
+            const uint64_t xa = reduce_draw2(w[4 * cb], w[4 * cb + 1]);
+            const uint64_t xb = reduce_draw2(w[4 * cb + 2], w[4 * cb + 3]);
             // DC = 1: batches beta0 .. beta0 + 3 (beta0 a multiple of 4): tiles E, O, E, O, rows row0, row0, row0 + 1, row0 + 1
             // DC = 2: batches beta0, beta0 + 1 (beta0 even): tiles E, E, O, O, chunks 0, 1, 0, 1 of row row0
             // DC % 4 == 0: one batch, chunks c0 .. c0 + 3
@@ -326,7 +347,10 @@ __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint
 // for): shares are folded and stored one at a time (tcgen05.ld.x8 per share and accumulator, the next share's loads in
 // flight under the current fold) instead of through N-wide unrolled register arrays.  packed_tc2n.cu instantiates it.
 template <int K, int T, int N, int ROUNDS, bool RTN = false>
-__global__ void __launch_bounds__(CTA2, RTN ? Shape2<K, T, N>::RESIDENT : 1)
+#ifndef SDA_TC2_TEMPLATED_MINB
+#define SDA_TC2_TEMPLATED_MINB 1
+#endif
+__global__ void __launch_bounds__(CTA2, RTN ? Shape2<K, T, N>::RESIDENT : SDA_TC2_TEMPLATED_MINB)
 packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
                         uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
                         const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,

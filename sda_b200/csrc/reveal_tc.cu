@@ -28,7 +28,7 @@ using namespace tc;
 constexpr int CTA = 128;
 
 // CH = 16-byte chunks per row = ceil(m' / 2) is a template parameter: the loads, the staging and the MMA issue of a tile
-// are straight-line code (the run-time-shaped first version spent 1 020 instructions per warp and tile, most of them
+// are straight-line code (the run-time-shaped first version spent 511 instructions per warp and tile, most of them
 // predicates and branches of its shape loops; profiles/r02_reveal.md).  k, the parity of m' and the TMEM allocation stay
 // run-time values.
 template <int CH>
