@@ -189,6 +189,17 @@ int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, s
 int sda_share_generate_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t secrets_ld,
                            size_t P, size_t dim, const uint8_t *seeds, int64_t *d_shares_out);
 
+/* The participant's two steps in one call for P participants (client/src/participate.rs:53-54: SecretMasker::mask, then
+ * :75-76: ShareGenerator::generate on the masked secrets): secrets[P][dim] (row stride secrets_ld), mask_rng_seeds[P][32]
+ * and share_rng_seeds[P][32] (HOST memory), masks_out[P][sda_mask_len(ms, dim)] (Full: the masks; ChaCha: the seed words;
+ * None: unused), shares_out[P][output_size][B].  Same results as sda_mask_dev followed by sda_share_generate_dev per
+ * participant.  Where both schemes are over 2^61-1 and the sharing scheme has an instantiated shape the masked secrets are
+ * never written to memory: the masks are drawn and added while the secrets are staged as operand rows of the share GEMM. */
+int sda_mask_share_generate_dev(sda_ctx *ctx, const sda_masking_scheme *ms, const sda_sharing_scheme *ss,
+                                const int64_t *d_secrets, size_t secrets_ld, size_t P, size_t dim,
+                                const uint8_t *mask_rng_seeds, const uint8_t *share_rng_seeds, int64_t *d_masks_out,
+                                int64_t *d_shares_out);
+
 /* ShareCombiner::combine: out[i] = sum_p shares[p*ld + i] mod m.  If d_acc_in != NULL it is
  * added as one more row (streaming tiles into a running sum: clerk.rs:71-72 FIXME). */
 int sda_share_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld, size_t P,

@@ -301,6 +301,19 @@ class Context:
         self.check(self._lib.sda_share_generate_dev(self._h, C.byref(scheme.c), _dev_ptr(d_secrets), secrets_ld, P, dim,
                                                     buf, _dev_ptr(d_shares_out)))
 
+    def mask_share_generate_dev(self, masking, sharing, d_secrets, secrets_ld, P, dim, mask_rng_seeds, share_rng_seeds,
+                                d_masks_out, d_shares_out):
+        """participate.rs:53-54 then :75-76 for P participants in one call: mask, then share the masked secrets (which are
+        never written to memory where the fused kernel applies).  Seeds are P x 32 bytes each."""
+        ms, sh = bytes(mask_rng_seeds), bytes(share_rng_seeds)
+        if len(ms) != 32 * P or len(sh) != 32 * P:
+            raise ValueError("mask_rng_seeds and share_rng_seeds must be P x 32 bytes")
+        mbuf = (C.c_uint8 * max(len(ms), 1)).from_buffer_copy(ms or b"\0")
+        sbuf = (C.c_uint8 * max(len(sh), 1)).from_buffer_copy(sh or b"\0")
+        self.check(self._lib.sda_mask_share_generate_dev(self._h, C.byref(masking.c), C.byref(sharing.c), _dev_ptr(d_secrets),
+                                                         secrets_ld, P, dim, mbuf, sbuf, _dev_ptr(d_masks_out),
+                                                         _dev_ptr(d_shares_out)))
+
     def share_combine_dev(self, scheme, d_shares, ld, P, L, d_out, d_acc_in=None):
         self.check(self._lib.sda_share_combine_dev(self._h, C.byref(scheme.c), _dev_ptr(d_shares), ld, P, L,
                                                    _dev_ptr(d_acc_in), _dev_ptr(d_out)))

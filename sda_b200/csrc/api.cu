@@ -83,7 +83,7 @@ struct sda_ctx {
     uint64_t nlaunch = 0;
     const char *kernel_name = "";
     std::string err;
-    DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image, tcg_image;
+    DevBuf in, out, aux, scratch, draws, keys, keys_pre, mat, tc_image, tc_image_r, tc2_image, tcg_image, masked_tmp;
     int packed_path = SDA_PACKED_PATH_AUTO;
     bool debug_force_reject = false;   // SDA_B200_DEBUG_FORCE_REJECT=1 at context creation: treat the fused kernel's flag as set
     std::vector<uint64_t> tc_image_key;   // (k, t, n, matrix) the device image was built for
@@ -972,7 +972,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     // goes back to the allocator
     for (DevBuf *b : {&ctx->keys, &ctx->keys_pre, &ctx->draws})
         if (b->p) cudaMemset(b->p, 0, b->cap);
-    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image, &ctx->tcg_image}) b->release();
+    for (DevBuf *b : {&ctx->in, &ctx->out, &ctx->aux, &ctx->scratch, &ctx->draws, &ctx->keys, &ctx->keys_pre, &ctx->mat, &ctx->tc_image, &ctx->tc_image_r, &ctx->tc2_image, &ctx->tcg_image, &ctx->masked_tmp}) b->release();
     ctx->stage[0].release();
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
@@ -1091,6 +1091,87 @@ int sda_share_generate_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int6
     DeviceGuard g(ctx->device);
     if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
     return share_generate_core(ctx, s, d_secrets, secrets_ld, P, dim, seeds, d_shares_out);
+}
+
+// participate.rs:53-54 then :75-76 for P participants: masks drawn and added while the secrets are staged as operand
+// rows (packed_tc2m.cu) where both schemes live over 2^61 - 1 and the sharing scheme has an instantiated shape; any other
+// pair of schemes, and a call in which gen_range rejected a word, runs mask and share generation one after the other per
+// participant with the masked secrets in a scratch vector.  Results are identical either way.
+int sda_mask_share_generate_dev(sda_ctx *ctx, const sda_masking_scheme *ms, const sda_sharing_scheme *ss,
+                                const int64_t *d_secrets, size_t secrets_ld, size_t P, size_t dim,
+                                const uint8_t *mask_rng_seeds, const uint8_t *share_rng_seeds, int64_t *d_masks_out,
+                                int64_t *d_shares_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
+    OK(mask_validate(ctx, ms));
+    Packed pk;
+    OK(validate(ctx, ss, &pk));
+    if (P == 0) return SDA_OK;
+    if (ms->kind == SDA_MASK_NONE) return share_generate_core(ctx, ss, d_secrets, secrets_ld, P, dim, share_rng_seeds, d_shares_out);
+    if (!mask_rng_seeds || !share_rng_seeds) return fail(ctx, SDA_ERR_INVALID, "null rng_seed");
+    if (ms->kind == SDA_MASK_CHACHA && ms->dimension != dim)   // chacha.rs:26
+        return fail(ctx, SDA_ERR_INVALID, "assertion failed: `(left == right)` (chacha.rs:26: scheme dimension %llu, %zu secrets)",
+                    (unsigned long long)ms->dimension, dim);
+    const size_t mask_len = sda_mask_len(ms, dim);
+    if (mask_len && !d_masks_out) return fail(ctx, SDA_ERR_INVALID, "null mask output");
+    const size_t out_per_p = ss->kind == SDA_SHARING_PACKED_SHAMIR ? (size_t)pk.n * ((dim + pk.k - 1) / pk.k) : (size_t)ss->share_count * dim;
+    const bool fused = dim > 0 && ss->kind == SDA_SHARING_PACKED_SHAMIR && (uint64_t)ms->modulus == P61 && pk.p == P61 &&
+                       tc_kernel_for(ctx, pk, dim) == TC_PAIRED && packed_share_tc2_masked_supported(pk.k, pk.t, pk.n, dim, ctx->rounds);
+    if (fused) {
+        // keys: [0, P) the sharing streams, [P, 2P) the mask streams (Full: the participant's rng itself, full.rs:24-27;
+        // ChaCha: the seed its rng draws first, chacha.rs:30-36, which is also the mask that is sent)
+        std::vector<ChaChaKey> k(2 * P);
+        std::vector<int64_t> words(ms->kind == SDA_MASK_CHACHA ? P * mask_len : 0);
+        for (size_t p = 0; p < P; p++) {
+            k[p] = key_from_seed_bytes(share_rng_seeds + 32 * p);
+            ChaChaKey mk = key_from_seed_bytes(mask_rng_seeds + 32 * p);
+            if (ms->kind == SDA_MASK_CHACHA) {
+                uint32_t blk[16], seed[8] = {0};
+                host_chacha_block(mk, 0, ctx->rounds, blk);
+                for (size_t i = 0; i < mask_len; i++) {
+                    seed[i] = blk[i];
+                    words[p * mask_len + i] = (int64_t)seed[i];
+                }
+                mk = key_from_words(seed, mask_len);
+            }
+            k[P + p] = mk;
+        }
+        Matrix M;
+        OK(share_matrix_cached(ctx, pk, &M));
+        CU(ctx->keys.reserve(2 * P * sizeof(ChaChaKey)));
+        CU(cudaMemcpyAsync(ctx->keys.p, k.data(), 2 * P * sizeof(ChaChaKey), cudaMemcpyHostToDevice, ctx->stream));
+        if (!words.empty())
+            CU(cudaMemcpyAsync(d_masks_out, words.data(), words.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));   // the host copies go out of scope
+        volatile uint32_t *wipe = reinterpret_cast<volatile uint32_t *>(k.data());
+        for (size_t i = 0; i < 2 * P * 8; i++) wipe[i] = 0;
+        OK(ensure_image(ctx, TC_PAIRED, pk, M, &ctx->tc2_image, &ctx->tc2_image_key));
+        CU(ctx->keys_pre.reserve(2 * packed_share_tc2_key_scratch_bytes(P)));
+        OK(clear_flags(ctx));
+        const ChaChaKey *d_keys = (const ChaChaKey *)ctx->keys.p;
+        CU(launch_packed_share_tc2_masked(ctx->lc(), pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim, d_keys, d_keys + P,
+                                          (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p,
+                                          ms->kind == SDA_MASK_FULL ? d_masks_out : nullptr, d_shares_out, ctx->d_flag));
+        unsigned rejected = 0;
+        OK(read_flags(ctx, &rejected, nullptr));
+        if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)
+        if (!rejected) return SDA_OK;
+    }
+    // one participant at a time through a scratch vector
+    CU(ctx->masked_tmp.reserve(std::max<size_t>(dim, 1) * sizeof(int64_t)));
+    int64_t *d_masked = (int64_t *)ctx->masked_tmp.p;
+    for (size_t p = 0; p < P; p++) {
+        int64_t words[8] = {0};
+        OK(mask_core(ctx, ms, d_secrets + p * secrets_ld, dim, mask_rng_seeds + 32 * p,
+                     ms->kind == SDA_MASK_FULL ? d_masks_out + p * mask_len : nullptr, words, d_masked));
+        if (ms->kind == SDA_MASK_CHACHA && mask_len) {
+            CU(cudaMemcpyAsync(d_masks_out + p * mask_len, words, mask_len * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        OK(share_generate_core(ctx, ss, d_masked, dim, 1, dim, share_rng_seeds + 32 * p, d_shares_out + p * out_per_p));
+    }
+    return SDA_OK;
 }
 
 int sda_share_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_shares, size_t ld, size_t P,

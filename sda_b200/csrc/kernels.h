@@ -109,6 +109,14 @@ size_t packed_share_tc2_key_scratch_bytes(size_t P);
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
                                     uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
+// mask -> share generation in one kernel (packed_tc2m.cu): both schemes over 2^61 - 1, 20 rounds, the instantiated shapes.
+// mask_keys[P]: the key of every participant's mask stream; mask_out: [P][dim] (Full scheme) or nullptr;
+// d_key_scratch: twice packed_share_tc2_key_scratch_bytes(P).  Whole vectors only.
+bool packed_share_tc2_masked_supported(int k, int t, int n, size_t dim, int rounds);
+cudaError_t launch_packed_share_tc2_masked(const LaunchCtx &lc, int k, int t, int n, const int64_t *secrets, size_t ld, size_t P,
+                                           size_t dim, const ChaChaKey *share_keys, const ChaChaKey *mask_keys,
+                                           uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *mask_out,
+                                           int64_t *shares_out, unsigned *flag);
 // the same kernel with the share count n <= 32 as a run-time value, per (k, t) with k <= 8, t <= 8 (packed_tc2n.cu);
 // 2^61 - 1 and 20 rounds only
 bool packed_share_tc2n_supported(int k, int t, int n, size_t dim, int rounds);

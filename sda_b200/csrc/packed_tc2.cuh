@@ -300,6 +300,70 @@ __device__ __forceinline__ void fill_secrets2(const int64_t *__restrict__ secret
     }
 }
 
+__device__ __forceinline__ void canon_pair2(uint32_t &lo, uint32_t &hi);
+
+// MASKED kernels (participate.rs:53-54 then :75-76 in one pass): the mask of every secret of pass (p, u) is drawn here and
+// added to the raw secrets where they lie in the staging buffer, so the masked secrets exist only as operand rows.
+// Element e of a participant takes draw e of its mask stream (full.rs:24-27, chacha.rs:38-41: one gen_range(0, m) per
+// secret): keystream block e / 8, a pass's PASS K / 8 blocks spread over the threads.  Over 2^61 - 1 a draw is
+// sd = (v & p) + (v >> 61) -- gen_range's value unless the low 61 bits of v are within 8 of 2^61 (a rejected word or a
+// wrap of the sum), which raises `flag` for the caller to redo the call on the exact path -- and a secret enters as any
+// u64 congruent to it: a negative one is canonicalised first, x + sd cannot overflow, and no reduction is needed (the
+// GEMM is linear in the bytes of its rows).  Elements at or beyond `dim` are the zero padding of the last batch
+// (batched.rs:38-43) and stay unmasked.  mask_row != nullptr: the Full scheme's mask vector of this participant.
+template <class S, int K, int ROUNDS>
+__device__ __forceinline__ void add_masks2(const KeyRegs &kr, uint32_t u, int tid, int64_t *sIn, size_t dim,
+                                           int64_t *__restrict__ mask_row, unsigned *flag) {
+    constexpr int NMB = S::PASS * K / 8;                          // mask blocks of a pass
+    uint32_t k[8], pre[12];
+    k[0] = kr.ka.x; k[1] = kr.ka.y; k[2] = kr.ka.z; k[3] = kr.ka.w;
+    k[4] = kr.kb.x; k[5] = kr.kb.y; k[6] = kr.kb.z; k[7] = kr.kb.w;
+    pre[0] = kr.pa.x; pre[1] = kr.pa.y; pre[2] = kr.pa.z; pre[3] = kr.pa.w;
+    pre[4] = kr.pb.x; pre[5] = kr.pb.y; pre[6] = kr.pb.z; pre[7] = kr.pb.w;
+    pre[8] = kr.pc.x; pre[9] = kr.pc.y; pre[10] = kr.pc.z; pre[11] = kr.pc.w;
+    const size_t e_pass = (size_t)u * (S::PASS * K);              // first element of the pass
+#pragma unroll 1
+    for (int nb = 0; nb < (NMB + CTA2 - 1) / CTA2; nb++) {
+        const uint32_t slot = nb * CTA2 + tid;
+        if constexpr (NMB % CTA2 != 0) {
+            if (slot >= (uint32_t)NMB) break;
+        }
+        uint32_t w[16];
+        chacha_block2<ROUNDS>(k, pre, u * (uint32_t)NMB + slot, w);
+        if (suspect_of_block(w) >= LOW29) {
+            bool bad = false;
+#pragma unroll
+            for (int d = 0; d < 8; d++) bad |= (w[2 * d] & LOW29) == LOW29 && w[2 * d + 1] >= 0xfffffff8u;
+            if (bad) atomicOr(flag, 1u);
+        }
+        int64_t *row = sIn + slot * 8;
+        const size_t e0 = e_pass + (size_t)slot * 8;
+#pragma unroll
+        for (int h = 0; h < 4; h++) {                             // two elements per 16-byte word
+            uint4 x = *reinterpret_cast<const uint4 *>(row + 2 * h);
+            uint64_t sd[2];
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const uint32_t w0 = w[4 * h + 2 * i], w1 = w[4 * h + 2 * i + 1];
+                sd[i] = pack(w1, w0 & LOW29) + (uint64_t)(w0 >> 29);
+                if (e0 + 2 * h + i >= dim) sd[i] = 0;             // padding of the last batch: no mask, no mask output
+            }
+            if ((int32_t)(x.y | x.w) < 0) {
+                canon_pair2(x.x, x.y);
+                canon_pair2(x.z, x.w);
+            }
+            uint32_t al, ah, bl, bh;
+            unpack(pack(x.x, x.y) + sd[0], al, ah);
+            unpack(pack(x.z, x.w) + sd[1], bl, bh);
+            *reinterpret_cast<uint4 *>(row + 2 * h) = make_uint4(al, ah, bl, bh);
+            if (mask_row != nullptr) {
+                if (e0 + 2 * h < dim) mask_row[e0 + 2 * h] = (int64_t)sd[0];
+                if (e0 + 2 * h + 1 < dim) mask_row[e0 + 2 * h + 1] = (int64_t)sd[1];
+            }
+        }
+    }
+}
+
 // one thread: the whole pass -- PASS batches x K secrets, contiguous in the participant's vector -- into the staging
 // buffer with one bulk copy; completion (by byte count) on `bar`
 template <class S, int K>
@@ -346,15 +410,17 @@ __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint
 // RTN: the share count is a run-time value n_rt <= N (N = the capacity the operand images and accumulators are sized
 // for): shares are folded and stored one at a time (tcgen05.ld.x8 per share and accumulator, the next share's loads in
 // flight under the current fold) instead of through N-wide unrolled register arrays.  packed_tc2n.cu instantiates it.
-template <int K, int T, int N, int ROUNDS, bool RTN = false>
+template <int K, int T, int N, int ROUNDS, bool RTN = false, bool MASKED = false>
 #ifndef SDA_TC2_TEMPLATED_MINB
 #define SDA_TC2_TEMPLATED_MINB 1
 #endif
-__global__ void __launch_bounds__(CTA2, RTN ? Shape2<K, T, N>::RESIDENT : SDA_TC2_TEMPLATED_MINB)
+__global__ void __launch_bounds__(CTA2, RTN || MASKED ? Shape2<K, T, N>::RESIDENT : SDA_TC2_TEMPLATED_MINB)
 packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t unit_begin,
                         uint32_t units_per_p, uint32_t units_total, uint32_t full_in_units, uint32_t full_out_units,
                         const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, const uint4 *__restrict__ b_image,
-                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok, uint32_t two16, uint32_t n_rt) {
+                        int64_t *__restrict__ out, unsigned *flag, int bulk_ok, int vec_ok, uint32_t two16, uint32_t n_rt,
+                        const ChaChaKey *__restrict__ mkeys = nullptr, const ChaChaPre *__restrict__ mpres = nullptr,
+                        int64_t *__restrict__ mask_out = nullptr) {
     typedef Shape2<K, T, N> S;
     static_assert(!RTN || S::ACC_BUFS == 2, "the run-time share count needs both accumulators of a pair at once");
     const uint32_t nsh = RTN ? n_rt : (uint32_t)N;         // shares per batch
@@ -414,6 +480,17 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
             fill_secrets2<S, K>(secrets, ld, dim, p, u, tid, sIn);
         }
         stage_draws2<S, ROUNDS>(load_keys2(keys, pres, p), u, tid, sD, flag);
+        if constexpr (MASKED) {
+            // the first pass's secrets are in place (landed, or written by their threads): mask them there
+            if (by_bulk(u)) {
+                mbar_wait(landed_bar, landed_parity);
+                landed_parity ^= 1;
+            } else {
+                __syncthreads();
+            }
+            add_masks2<S, K, ROUNDS>(load_keys2(mkeys, mpres, p), u, tid, sIn, dim,
+                                     mask_out != nullptr ? mask_out + (size_t)p * dim : nullptr, flag);
+        }
     }
 
     for (uint32_t unit = blockIdx.x; unit < units_total; unit += gridDim.x) {
@@ -428,7 +505,9 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         if (more) knext = load_keys2(keys, pres, pn);
         // ---- this thread's 2K secrets of every pair (batches 2 tid, 2 tid + 1 of the pair): K aligned 16-byte words
         //      of the raw vector, which are the operand chunks as they are -------------------------------------------
-        if (by_bulk(u)) {
+        if constexpr (MASKED) {
+            __syncthreads();                     // the masked secrets were written by other threads (add_masks2)
+        } else if (by_bulk(u)) {
             mbar_wait(landed_bar, landed_parity);
             landed_parity ^= 1;
         }
@@ -441,14 +520,16 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         }
 #pragma unroll
         for (int q = 0; q < S::PAIRS; q++) {
-            uint32_t sign = 0;
+            if constexpr (!MASKED) {             // (masked rows are non-negative sums already, up to 64 bits wide)
+                uint32_t sign = 0;
 #pragma unroll
-            for (int i = 0; i < K; i++) sign |= v[q][i].y | v[q][i].w;
-            if ((int32_t)sign < 0) {
+                for (int i = 0; i < K; i++) sign |= v[q][i].y | v[q][i].w;
+                if ((int32_t)sign < 0) {
 #pragma unroll
-                for (int i = 0; i < K; i++) {
-                    canon_pair2(v[q][i].x, v[q][i].y);
-                    canon_pair2(v[q][i].z, v[q][i].w);
+                    for (int i = 0; i < K; i++) {
+                        canon_pair2(v[q][i].x, v[q][i].y);
+                        canon_pair2(v[q][i].z, v[q][i].w);
+                    }
                 }
             }
             uint8_t *te = sS + (2 * q) * S::S_TILE + (tid >> 3) * S::SBO_S + (tid & 7) * 16;
@@ -479,6 +560,16 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
         if (more) {
             stage_draws2<S, ROUNDS>(knext, un, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
             if (!by_bulk(un)) fill_secrets2<S, K>(secrets, ld, dim, pn, un, tid, sIn);
+            if constexpr (MASKED) {
+                if (by_bulk(un)) {
+                    mbar_wait(landed_bar, landed_parity);
+                    landed_parity ^= 1;
+                } else {
+                    __syncthreads();
+                }
+                add_masks2<S, K, ROUNDS>(load_keys2(mkeys, mpres, pn), un, tid, sIn, dim,
+                                         mask_out != nullptr ? mask_out + (size_t)pn * dim : nullptr, flag);
+            }
         }
 
         // ---- per pair: D = A . B^T on the tensor core, then compose the shares of batches 2 tid and 2 tid + 1 ------
@@ -678,10 +769,13 @@ void build_b_image2(const Matrix &m, uint64_t p, uint8_t *img, int n_rt = N) {
                     }
 }
 
-template <int K, int T, int N, int ROUNDS, bool RTN = false>
+// MASKED: mkeys = the participants' mask keys, d_pre holds 2 P entries (sharing keys, then mask keys), mask_out = the
+// Full scheme's mask vectors [P][dim] or nullptr; first_batch must be 0 and n_batches cover the vector (a mask stream is
+// consumed from its first draw)
+template <int K, int T, int N, int ROUNDS, bool RTN = false, bool MASKED = false>
 cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, size_t first_batch,
                     size_t n_batches, const ChaChaKey *keys, uint32_t *d_pre, const uint8_t *d_b_image, int64_t *out,
-                    unsigned *flag, int n_rt = N) {
+                    unsigned *flag, int n_rt = N, const ChaChaKey *mkeys = nullptr, int64_t *mask_out = nullptr) {
     typedef Shape2<K, T, N> S;
     const size_t B = (dim + K - 1) / K;
     if (first_batch % S::PASS != 0 || first_batch > B) return cudaErrorInvalidValue;
@@ -691,7 +785,8 @@ cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size
     const size_t units_total = units_per_p * P;
     if (units_total == 0) return cudaSuccess;
     if ((unit_begin + units_per_p) >> 31 || units_total >> 31 || P >> 31) return cudaErrorInvalidValue;
-    auto kern = packed_share_tc2_kernel<K, T, N, ROUNDS, RTN>;
+    auto kern = packed_share_tc2_kernel<K, T, N, ROUNDS, RTN, MASKED>;
+    if (MASKED && (mkeys == nullptr || first_batch != 0 || ((dim + 7) / 8) >> 32)) return cudaErrorInvalidValue;
     // never more CTAs on an SM than can hold their TMEM columns (tc_common.cuh)
     // RTN: one more pair of operand images per further group of N shares
     const size_t n_groups = RTN ? ((size_t)n_rt + N - 1) / N : 1;
@@ -717,10 +812,15 @@ cudaError_t launch2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size
     ChaChaPre *pres = reinterpret_cast<ChaChaPre *>(d_pre);
     chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
     ++*lc.nlaunch;
+    if (MASKED) {
+        chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(mkeys, P, pres + P);
+        ++*lc.nlaunch;
+    }
     kern<<<(unsigned)grid, CTA2, smem, lc.stream>>>(secrets, ld, dim, B, (uint32_t)unit_begin, (uint32_t)units_per_p,
                                                     (uint32_t)units_total, (uint32_t)std::min<size_t>(full_in, 0xffffffffu),
                                                     (uint32_t)std::min<size_t>(full_out, 0xffffffffu), keys, pres,
-                                                    reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok, 65536u, (uint32_t)n_rt);
+                                                    reinterpret_cast<const uint4 *>(d_b_image), out, flag, bulk_ok, vec_ok, 65536u, (uint32_t)n_rt,
+                                                    mkeys, MASKED ? pres + P : nullptr, mask_out);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }

@@ -452,3 +452,90 @@ def test_fused_in_place_redo_does_not_double_count(oracle, torch_cuda, monkeypat
     assert np.array_equal(results[1], exp)
     plain.close()
     forced.close()
+
+
+@pytest.mark.parametrize("sharing", ["cfg3", "cfg4", "cfg5", "k4t2n6", "additive3", "cfg3_generic_prime"])
+@pytest.mark.parametrize("mask_kind", ["full", "chacha", "none"])
+@pytest.mark.parametrize("offset,ld_pad", [(0, 0), (1, 1)])
+def test_mask_share_generate_matches_mask_then_generate(ctx, oracle, torch_cuda, sharing, mask_kind, offset, ld_pad):
+    """sda_mask_share_generate_dev == SecretMasker::mask then ShareGenerator::generate per participant (oracle): the fused
+    kernel (masks added in shared memory; BASELINE shapes over 2^61-1) and the unfused path behind the same entry point
+    (another shape, additive sharing, another prime), Full / ChaCha / no masking, aligned and unaligned sources, vectors
+    that end inside a pass and inside a batch, negative secrets"""
+    t = torch_cuda
+    if sharing == "k4t2n6":
+        ss = util.packed_scheme(P61, 4, 2, 6, oracle)
+    elif sharing == "additive3":
+        ss = LSS.Additive(3, P61)
+    elif sharing == "cfg3_generic_prime":
+        ss = util.packed_scheme(params.P61_GENERIC, 3, 2, 5, oracle)
+    else:
+        ss = {"cfg3": params.config3, "cfg4": params.config4, "cfg5": params.config5}[sharing]()
+    p = ss.modulus
+    k = ss.input_size()
+    packed = sharing != "additive3"
+    rng = np.random.default_rng(len(sharing) + len(mask_kind))
+    for P, dim in [(1, 1), (3, 512 * k * 3 + 2 * k + 1), (2, 1024 * k), (2, 7)]:
+        ms = {"full": LMS.Full(p), "chacha": LMS.ChaCha(p, dim, 128), "none": LMS.None_()}[mask_kind]
+        ld = dim + (dim & 1) + ld_pad
+        secrets = rng.integers(0, p, size=(P, dim), dtype=np.int64)
+        secrets[-1, ::3] = rng.integers(-(1 << 62), 1 << 62, size=secrets[-1, ::3].shape, dtype=np.int64)
+        flat = np.zeros(offset + P * ld, dtype=np.int64)
+        for pi in range(P):
+            flat[offset + pi * ld: offset + pi * ld + dim] = secrets[pi]
+        mseeds = b"".join(util.seed_bytes(f"mk/{sharing}/{P}/{dim}/{pi}") for pi in range(P))
+        sseeds = b"".join(util.seed_bytes(f"sh/{sharing}/{P}/{dim}/{pi}") for pi in range(P))
+        mask_len = {"full": dim, "chacha": 4, "none": 0}[mask_kind]
+        n_out = ss.output_size() * (ss.batches(dim) if packed else dim)
+        d_masks = t.full((P, max(mask_len, 1)), -1, dtype=t.int64, device="cuda")
+        d_shares = t.empty((P, n_out), dtype=t.int64, device="cuda")
+        ctx.mask_share_generate_dev(ms, ss, dev(t, flat)[offset:], ld, P, dim, mseeds, sseeds, d_masks, d_shares)
+        ctx.synchronize()
+        fused = mask_kind != "none" and sharing in ("cfg3", "cfg4", "cfg5")
+        assert ("mask+packed_share" in ctx.last_kernel()) == fused, ctx.last_kernel()
+        got_m, got_s = host(d_masks), host(d_shares)
+        for pi in range(P):
+            if mask_kind == "none":
+                exp_s = util.oracle_generate(oracle, ss, secrets[pi], sseeds[32 * pi:32 * pi + 32], matrix=packed)
+                exp_m = np.zeros(0, dtype=np.int64)
+            else:
+                mo = util.to_oracle_masking(oracle, ms)
+                emask, emasked = oracle.mask(mo, secrets[pi], oracle.rng_from_seed_bytes(mseeds[32 * pi:32 * pi + 32]))
+                exp_m = np.asarray(emask, dtype=np.int64)
+                exp_s = util.oracle_generate(oracle, ss, np.asarray(emasked, dtype=np.int64), sseeds[32 * pi:32 * pi + 32],
+                                             matrix=packed)
+            assert np.array_equal(got_s[pi], util.canon(oracle, p, np.asarray(exp_s)).reshape(-1)), (sharing, mask_kind, P, dim, pi)
+            assert np.array_equal(got_m[pi, :mask_len], exp_m), (sharing, mask_kind, P, dim, pi)
+
+
+def test_mask_share_generate_redo_after_rejection(oracle, torch_cuda, monkeypatch):
+    """the fused mask -> share kernel with its rejection flag forced: the call is redone on the unfused path and returns the
+    same masks and shares"""
+    import sda_b200
+    t = torch_cuda
+    ss, dim, P = params.config3(), 5000, 3
+    ms = LMS.Full(ss.modulus)
+    rng = np.random.default_rng(5)
+    secrets = rng.integers(0, ss.modulus, size=(P, dim), dtype=np.int64)
+    mseeds = b"".join(util.seed_bytes(f"rm/{pi}") for pi in range(P))
+    sseeds = b"".join(util.seed_bytes(f"rs/{pi}") for pi in range(P))
+    plain = sda_b200.Context(0)
+    monkeypatch.setenv("SDA_B200_DEBUG_FORCE_REJECT", "1")
+    forced = sda_b200.Context(0)
+    monkeypatch.delenv("SDA_B200_DEBUG_FORCE_REJECT")
+    res = []
+    for c in (plain, forced):
+        d_masks = t.empty((P, dim), dtype=t.int64, device="cuda")
+        d_shares = t.empty((P, ss.output_size(), ss.batches(dim)), dtype=t.int64, device="cuda")
+        c.mask_share_generate_dev(ms, ss, dev(t, secrets), dim, P, dim, mseeds, sseeds, d_masks, d_shares)
+        c.synchronize()
+        res.append((host(d_masks), host(d_shares), c.last_kernel()))
+    assert "mask+packed_share" in res[0][2] and "mask+packed_share" not in res[1][2]
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    mo = util.to_oracle_masking(oracle, ms)
+    emask, emasked = oracle.mask(mo, secrets[1], oracle.rng_from_seed_bytes(mseeds[32:64]))
+    assert np.array_equal(res[0][0][1], np.asarray(emask, dtype=np.int64))
+    exp = util.oracle_generate(oracle, ss, np.asarray(emasked, dtype=np.int64), sseeds[32:64], matrix=True)
+    assert np.array_equal(res[0][1][1], util.canon(oracle, ss.modulus, exp))
+    plain.close()
+    forced.close()

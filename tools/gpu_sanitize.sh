@@ -24,4 +24,11 @@ timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pyte
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py tests/test_gpu_codec.py -q -m gpu \
   -k "(run_time_share_count and shape6 and 0-0) or (reveal_many_tiles and cfg3 and 0) or varint_known or varint_encode_decode" \
   > gpurun_out/sanitize_racecheck_r02b.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_r02b.log
+# the fused mask -> share kernel (masks added in place in the staging buffer)
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
+  -k "mask_share_generate_matches and (cfg3 or cfg4) and (full or chacha)" > gpurun_out/sanitize_memcheck_masked.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_masked.log
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
+  -k "mask_share_generate_matches and cfg3 and full" > gpurun_out/sanitize_racecheck_masked.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_masked.log
+timeout 1500 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
+  -k "mask_share_generate_matches and cfg5 and full" > gpurun_out/sanitize_synccheck_masked.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_synccheck_masked.log
 (echo "compute-sanitizer on a B200 (tools/gpu_sanitize.sh), round 2"; for f in gpurun_out/sanitize_*.log; do echo "== $(basename $f)"; grep -v "^$" $f | tail -6; done) > gpurun_out/r02_sanitizer.txt

@@ -115,6 +115,23 @@ def main():
                        lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n * B) * 8,
                        f"8(1+n/k) = {8 * (1 + n / s.input_size()):.2f} B per secret")
             ctx.set_packed_path(0)
+            if "cfg3" in name or "cfg5" in name:
+                # the participant's two steps (participate.rs:53-54, :75-76): Full mask then share generation, as two
+                # entry points (P mask calls, masked secrets through HBM) and as the one fused kernel
+                ms = LMS.Full(P61)
+                masks, masked = empty(P, dim), empty(P, dim)
+                msd = seeds(name + "/mask", P)
+                alg = P * (2 * dim + n * B) * 8            # secrets in, masks and shares out
+
+                def two_steps():
+                    for pi in range(P):
+                        ctx.mask_dev(ms, sec[pi], dim, msd[32 * pi:32 * pi + 32], masks[pi], masked[pi])
+                    ctx.share_generate_dev(s, masked, dim, P, dim, sd, sh)
+                timeit(f"full mask, then packed_share {name} [{P}][10M] (P + 1 calls, masked secrets through HBM)", two_steps,
+                       P * dim, alg)
+                timeit(f"mask+packed_share {name} [{P}][10M] (one kernel, masked secrets in shared memory only)",
+                       lambda: ctx.mask_share_generate_dev(ms, s, sec, dim, P, dim, msd, sd, masks, sh), P * dim, alg)
+                del masks, masked
             if "cfg4" in name:
                 out = empty(B)
                 timeit("combine cfg4 clerk job [128][2M] (strided view)",
