@@ -175,6 +175,13 @@ int sda_mask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *secrets, 
  * scheme.dimension) elements. */
 int sda_mask_combine(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *masks, size_t P, size_t mask_len,
                      int64_t *out, size_t *out_len);
+/* The participant's two steps in one call (client/src/participate.rs:53-54 SecretMasker::mask, then :75-76
+ * ShareGenerator::generate on the masked secrets): mask_out[sda_mask_len(ms, dim)], shares_out[output_size][B].  Same
+ * results as sda_mask followed by sda_share_generate; the masked secrets stay on the device (never cross the link, and
+ * where sda_mask_share_generate_dev's fused kernel applies never reach its memory either). */
+int sda_mask_share_generate(sda_ctx *ctx, const sda_masking_scheme *ms, const sda_sharing_scheme *ss, const int64_t *secrets,
+                            size_t dim, const uint8_t mask_rng_seed[32], const uint8_t share_rng_seed[32], int64_t *mask_out,
+                            int64_t *shares_out);
 /* SecretUnmasker::unmask on (mask, masked). */
 int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, size_t mask_len,
                const int64_t *masked, size_t dim, int64_t *out);

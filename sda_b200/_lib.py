@@ -66,6 +66,7 @@ PROTOTYPES = {
     "sda_mask_combine": (_int, [_vp, _ms, _vp, _sz, _sz, _vp, _psz]),
     "sda_unmask": (_int, [_vp, _ms, _vp, _sz, _vp, _sz, _vp]),
     "sda_share_generate_dev": (_int, [_vp, _ss, _vp, _sz, _sz, _sz, _vp, _vp]),
+    "sda_mask_share_generate": (_int, [_vp, _ms, _ss, _vp, _sz, _vp, _vp, _vp, _vp]),
     "sda_mask_share_generate_dev": (_int, [_vp, _ms, _ss, _vp, _sz, _sz, _sz, _vp, _vp, _vp, _vp]),
     "sda_share_combine_dev": (_int, [_vp, _ss, _vp, _sz, _sz, _sz, _vp, _vp]),
     "sda_share_generate_combine_dev": (_int, [_vp, _ss, _vp, _sz, _sz, _sz, _vp, _vp, _vp]),

@@ -230,6 +230,19 @@ class Context:
                                                 _ptr(out)))
         return out
 
+    def mask_share_generate(self, masking, sharing, secrets, mask_rng_seed=None, share_rng_seed=None):
+        """participate.rs:53-54 then :75-76 in one call: (mask, shares[output_size][B]); the masked secrets stay on the
+        device.  Same results as `mask` followed by `share_generate`."""
+        sec = _i64(secrets)
+        dim = len(sec)
+        n, B = sharing.output_size(), sharing.batches(dim)
+        ml = masking.mask_len(dim)
+        mk = np.empty(max(ml, 1), dtype=np.int64)
+        out = np.empty((n, B), dtype=np.int64)
+        self.check(self._lib.sda_mask_share_generate(self._h, C.byref(masking.c), C.byref(sharing.c), _ptr(sec), dim,
+                                                     _seed(mask_rng_seed), _seed(share_rng_seed), _ptr(mk), _ptr(out)))
+        return mk[:ml], out
+
     def share_combine(self, scheme, shares, out=None):
         """shares: 2-D array [P][L] (contiguous fast path) or a list of 1-D rows (`Vec<Vec<Share>>`)."""
         if isinstance(shares, np.ndarray) and shares.ndim == 2 and shares.dtype == np.int64:

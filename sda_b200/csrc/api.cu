@@ -1548,6 +1548,33 @@ int sda_share_generate(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t 
     return d2h(ctx, shares_out, ctx->out.p, n * B * sizeof(int64_t));
 }
 
+// participate.rs:53-54 then :75-76 on host vectors: one upload of the secrets, the fused kernel (or the two steps on the
+// device), one download of the mask and of the shares -- the masked secrets never cross the link (the two trait calls
+// one after the other move them down and up again: 16 of 45 bytes per secret with a Full mask)
+int sda_mask_share_generate(sda_ctx *ctx, const sda_masking_scheme *ms, const sda_sharing_scheme *ss, const int64_t *secrets,
+                            size_t dim, const uint8_t mask_rng_seed[32], const uint8_t share_rng_seed[32], int64_t *mask_out,
+                            int64_t *shares_out) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    OK(mask_validate(ctx, ms));
+    OK(validate(ctx, ss, nullptr));
+    if (dim == 0 && ms->kind != SDA_MASK_CHACHA) return SDA_OK;
+    const size_t mask_len = sda_mask_len(ms, dim);
+    const size_t out_len = ss->kind == SDA_SHARING_PACKED_SHAMIR ? (size_t)ss->share_count * sda_share_batches(ss, dim)
+                                                                 : (size_t)ss->share_count * dim;
+    if ((dim && (!secrets || !shares_out)) || (mask_len && !mask_out)) return fail(ctx, SDA_ERR_INVALID, "null buffer");
+    const size_t ldp = (dim + 3) & ~(size_t)3;
+    CU(ctx->in.reserve(std::max<size_t>(ldp, 4) * sizeof(int64_t)));
+    CU(ctx->out.reserve(std::max<size_t>(out_len, 1) * sizeof(int64_t)));
+    CU(ctx->aux.reserve(std::max<size_t>(mask_len, 1) * sizeof(int64_t)));
+    if (dim) OK(h2d(ctx, ctx->in.p, secrets, dim * sizeof(int64_t)));
+    OK(sda_mask_share_generate_dev(ctx, ms, ss, (const int64_t *)ctx->in.p, ldp, 1, dim, mask_rng_seed, share_rng_seed,
+                                   (int64_t *)ctx->aux.p, (int64_t *)ctx->out.p));
+    if (mask_len) OK(d2h(ctx, mask_out, ctx->aux.p, mask_len * sizeof(int64_t)));
+    if (out_len) OK(d2h(ctx, shares_out, ctx->out.p, out_len * sizeof(int64_t)));
+    return SDA_OK;
+}
+
 // streamed combine of a host matrix: tiles of rows through ctx->in, running sum in ctx->out
 static int combine_host(sda_ctx *ctx, int64_t modulus, const int64_t *shares, const int64_t *const *rows, size_t P,
                         size_t L, int64_t *out) {

@@ -43,6 +43,16 @@ static int full_loop(sda_ctx *ctx, const char *name, const sda_sharing_scheme *s
         if (got_ml != ml) return fprintf(stderr, "%s: mask length %zu != %zu\n", name, got_ml, ml), 1;
         seed_for(seed, 2, (int)p);
         CHECK(sda_share_generate(ctx, ss, masked, dim, seed, shares + p * n * B));                    /* participate.rs:75-76 */
+        /* the same two steps through the one-call fast path: identical mask and shares */
+        int64_t *mask2 = calloc(ml + 1, sizeof(int64_t)), *shares2 = calloc(n * B + 1, sizeof(int64_t));
+        uint8_t mseed[32];
+        seed_for(mseed, 1, (int)p);
+        CHECK(sda_mask_share_generate(ctx, ms, ss, secrets + p * dim, dim, mseed, seed, mask2, shares2));
+        int differ = memcmp(mask2, masks + p * ml, ml * sizeof(int64_t)) != 0 ||
+                     memcmp(shares2, shares + p * n * B, n * B * sizeof(int64_t)) != 0;
+        free(mask2);
+        free(shares2);
+        if (differ) return fprintf(stderr, "%s: sda_mask_share_generate differs from mask + share_generate\n", name), 1;
     }
     for (size_t c = 0; c < n; c++) {                                                                  /* clerk.rs:85-86 */
         const int64_t **rows = malloc(P * sizeof *rows);

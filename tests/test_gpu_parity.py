@@ -396,3 +396,26 @@ def test_scheme_validation(crypto):
     with pytest.raises(SdaClientError, match="primitive 8-th root"):
         crypto.new_share_generator(LSS.PackedShamir(3, 8, 4, 433, 151, 150))
     crypto.new_share_generator(LSS.PackedShamir(3, 8, 4, 433, 354, 150))
+
+
+@pytest.mark.parametrize("name,mk", PACKED + [("additive3", lambda: LSS.Additive(3, P61))], ids=[p[0] for p in PACKED] + ["additive3"])
+@pytest.mark.parametrize("mask_kind", ["full", "chacha", "none"])
+def test_mask_share_generate_host(ctx, oracle, name, mk, mask_kind):
+    """sda_mask_share_generate on host vectors == mask then share_generate through the separate trait calls (and the
+    oracle): every masking scheme, packed (fused kernel for the 2^61-1 shapes, two steps for p = 433) and additive sharing"""
+    ss = mk()
+    p = ss.modulus
+    rng = np.random.default_rng(len(name))
+    for dim in (1, 7, 1000, 4099):
+        ms = {"full": LMS.Full(p), "chacha": LMS.ChaCha(p, dim, 64), "none": LMS.None_()}[mask_kind]
+        secrets = util.rand_secrets(rng, dim, p, "signed" if p > 433 else "canonical")
+        mseed, sseed = util.seed_bytes(f"hm/{name}/{dim}"), util.seed_bytes(f"hs/{name}/{dim}")
+        mask, shares = ctx.mask_share_generate(ms, ss, secrets, mseed, sseed)
+        if mask_kind == "none":
+            emask, emasked = np.zeros(0, dtype=np.int64), secrets
+        else:
+            emask, emasked = ctx.mask(ms, secrets, mseed)
+            omask, omasked = oracle.mask(util.to_oracle_masking(oracle, ms), secrets, oracle.rng_from_seed_bytes(mseed))
+            assert np.array_equal(emask, np.asarray(omask, dtype=np.int64))
+        assert np.array_equal(mask, emask), (name, mask_kind, dim)
+        assert np.array_equal(shares, ctx.share_generate(ss, emasked, sseed)), (name, mask_kind, dim)
