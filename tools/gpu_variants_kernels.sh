@@ -1,4 +1,5 @@
 #!/bin/bash
+# usage: bash tools/gpu_variants_kernels.sh name1 name2 ...   (variants built by tools/build_variant.sh)
 # GPU job: kernel-table lines of the templated shapes for the library and for build variants, then the share-gen cycle counts
 mkdir -p gpurun_out
 for v in base "$@"; do
