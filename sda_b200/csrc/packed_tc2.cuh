@@ -411,6 +411,9 @@ __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint
 // for): shares are folded and stored one at a time (tcgen05.ld.x8 per share and accumulator, the next share's loads in
 // flight under the current fold) instead of through N-wide unrolled register arrays.  packed_tc2n.cu instantiates it.
 template <int K, int T, int N, int ROUNDS, bool RTN = false, bool MASKED = false>
+#ifndef SDA_TC2_RTN_CHUNK
+#define SDA_TC2_RTN_CHUNK 1          // the run-time share count folds four shares per TMEM load and wait (0: one at a time, pipelined: 1-10 % slower)
+#endif
 #ifndef SDA_TC2_TEMPLATED_MINB
 #define SDA_TC2_TEMPLATED_MINB 1
 #endif
@@ -606,6 +609,27 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                     mbar_wait(full_bar, parity);
                     parity ^= 1;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#if SDA_TC2_RTN_CHUNK
+                    // four shares at a time (one 32-column load per accumulator, one wait), then the rest singly
+                    uint32_t j4 = 0;
+#pragma unroll 1
+                    for (; j4 + 4 <= nsg; j4 += 4) {
+                        uint32_t de[4][8], dd[4][8];
+                        tmem_ld32(ta + 8 * j4, &de[0][0]);
+                        tmem_ld32(tb + 8 * j4, &dd[0][0]);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int i = 0; i < 4; i++) put(de[i], dd[i]);
+                    }
+#pragma unroll 1
+                    for (; j4 < nsg; j4++) {
+                        uint32_t e0[8], o0[8];
+                        tmem_ld8(ta + 8 * j4, e0);
+                        tmem_ld8(tb + 8 * j4, o0);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        put(e0, o0);
+                    }
+#else
                     uint32_t e0[8], o0[8], e1[8], o1[8];
                     tmem_ld8(ta, e0);
                     tmem_ld8(tb, o0);
@@ -626,6 +650,7 @@ packed_share_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t d
                             put(e1, o1);
                         }
                     }
+#endif
                     // the accumulators are read out: the next group of this pair, or the first group of the next pair
                     const bool next_group = g + 1 < ngroups;
                     if (next_group || q + 1 < S::PAIRS) {
