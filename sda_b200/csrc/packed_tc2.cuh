@@ -407,9 +407,9 @@ __device__ __forceinline__ void store_pair(const uint32_t (&d)[N][8], const uint
     }
 }
 
-// RTN: the share count is a run-time value n_rt <= N (N = the capacity the operand images and accumulators are sized
-// for): shares are folded and stored one at a time (tcgen05.ld.x8 per share and accumulator, the next share's loads in
-// flight under the current fold) instead of through N-wide unrolled register arrays.  packed_tc2n.cu instantiates it.
+// RTN: the share count is a run-time value; the operand images and accumulators are sized for groups of N shares, and a
+// group is folded and stored four shares per 32-column tcgen05.ld, then singly, instead of through N-wide unrolled register
+// arrays.  packed_tc2n.cu instantiates it.  MASKED: see add_masks2.
 template <int K, int T, int N, int ROUNDS, bool RTN = false, bool MASKED = false>
 #ifndef SDA_TC2_RTN_CHUNK
 #define SDA_TC2_RTN_CHUNK 1          // the run-time share count folds four shares per TMEM load and wait (0: one at a time, pipelined: 1-10 % slower)

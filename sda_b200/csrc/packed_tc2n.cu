@@ -2,7 +2,7 @@
 // instantiated for every (k, t) with k + t <= 16 (120 kernels), p = 2^61 - 1, ChaCha20.  Operand images and accumulators
 // are sized for 8 shares (two 64-column accumulators, the TMEM footprint of the fully templated shapes); a scheme with
 // more shares, up to 32, runs its shares through the accumulators in groups of 8, one pair of operand images per group.
-// A scheme here runs at nearly the speed of a fully templated shape (the fold loses its unrolled 32-column TMEM loads;
+// A scheme here runs at nearly the speed of a fully templated shape (the fold takes four shares per TMEM load instead of n;
 // odd t stores its draws 8 bytes at a time); other primes and 8 / 12 rounds take the run-time-shaped kernel of
 // packed_tcg.cu.
 //
