@@ -605,11 +605,12 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
         exact = rejected != 0;
     } else if (fast) {
         OK(clear_flags(ctx));
+        if (additive) CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(std::min<size_t>(P, 65535))));
         for (size_t p0 = 0; p0 < P; p0 += 65535) {
             const size_t pc = std::min<size_t>(65535, P - p0);
             if (additive)
                 CU(launch_additive_split(ctx->lc(), f, dr, ctx->rounds, n, d_secrets + p0 * ld, ld, pc, dim, d_keys + p0,
-                                         nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag));
+                                         nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag, (uint32_t *)ctx->keys_pre.p));
             else
                 CU(launch_packed_share(ctx->lc(), f, dr, ctx->rounds, pk.k, pk.t, pk.n, M, d_secrets + p0 * ld, ld, pc,
                                        dim, d_keys + p0, nullptr, nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag));
@@ -1218,9 +1219,10 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
                 CU(ctx->aux.reserve(n * B * sizeof(int64_t)));
                 d_dst = (int64_t *)ctx->aux.p;
             }
+            CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
             CU(launch_packed_share_combine_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
                                               (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_acc_in,
-                                              d_dst, ctx->d_flag));
+                                              d_dst, ctx->d_flag, (uint32_t *)ctx->keys_pre.p));
             unsigned rejected = 0;
             OK(read_flags(ctx, &rejected, nullptr));
             if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)

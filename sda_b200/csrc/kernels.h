@@ -50,7 +50,8 @@ cudaError_t launch_submod(const LaunchCtx &lc, const FieldParams &f, const int64
 cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
                                   int n, const int64_t *secrets, size_t ld, size_t P, size_t dim,
                                   const ChaChaKey *keys, const uint64_t *draws, int64_t *shares_out,
-                                  unsigned *flag);
+                                  unsigned *flag, uint32_t *d_key_scratch = nullptr);
+// d_key_scratch (optional): packed_share_tc2_key_scratch_bytes(P) bytes for the keys' first-round constants (chacha_pre.cuh)
 // mask_out (may be null) [dim], masked_out [dim]: Full mask (full.rs:24-31) and the
 // participant side of the ChaCha mask (chacha.rs:36-45)
 cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
@@ -138,7 +139,8 @@ cudaError_t launch_packed_share_tcg(const LaunchCtx &lc, const FieldParams &f, c
 // fused: out[n][B] = acc_in[n][B] + sum over the P participants of their shares, accumulated in TMEM
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
-                                           const int64_t *acc_in, int64_t *out, unsigned *flag);
+                                           const int64_t *acc_in, int64_t *out, unsigned *flag,
+                                           uint32_t *d_key_scratch = nullptr);
 // true when launch_packed_share / launch_additive_split have an in-kernel-rng instantiation
 bool packed_share_has_fast_path(int k, int t, int n);
 bool additive_split_has_fast_path(int n);

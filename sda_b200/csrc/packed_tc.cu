@@ -42,6 +42,7 @@
 #include <algorithm>
 #include <cstring>
 
+#include "chacha_pre.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -540,20 +541,30 @@ __device__ __forceinline__ uint64_t compose_wide(const uint32_t (&d)[8]) {
     return v >= P61 ? v - P61 : v;
 }
 
+// pres != nullptr: the participants' precomputed first-round constants (chacha_pre.cuh); the launcher passes them when
+// every block counter of the launch is below 2^32
 template <class F, int ROUNDS>
-__device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ keys, size_t p, size_t r, int warp, int lane,
-                                                  uint8_t *sD, unsigned *flag) {
+__device__ __forceinline__ void stage_draws_fused(const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres, size_t p,
+                                                  size_t r, int warp, int lane, uint8_t *sD, unsigned *flag) {
     typedef typename F::S S;
-    uint32_t k[8];
+    uint32_t k[8], pre[12];
     const uint4 *src = reinterpret_cast<const uint4 *>(keys + p);
     const uint4 ka = __ldg(src), kb = __ldg(src + 1);
     k[0] = ka.x; k[1] = ka.y; k[2] = ka.z; k[3] = ka.w;
     k[4] = kb.x; k[5] = kb.y; k[6] = kb.z; k[7] = kb.w;
+    if (pres != nullptr) {
+        const uint4 *ps = reinterpret_cast<const uint4 *>(pres + p);
+        const uint4 pa = __ldg(ps), pb = __ldg(ps + 1), pc = __ldg(ps + 2);
+        pre[0] = pa.x; pre[1] = pa.y; pre[2] = pa.z; pre[3] = pa.w;
+        pre[4] = pb.x; pre[5] = pb.y; pre[6] = pb.z; pre[7] = pb.w;
+        pre[8] = pc.x; pre[9] = pc.y; pre[10] = pc.z; pre[11] = pc.w;
+    }
 #pragma unroll 1
     for (int nb = 0; nb < F::NBW; nb++) {
         const uint32_t blk = nb * 32 + lane;                       // block of this tile, in stream order
         uint32_t w[16];
-        chacha_block<ROUNDS>(k, r * (size_t)(16 * S::kT) + blk, w);
+        if (pres != nullptr) chacha_block2<ROUNDS>(k, pre, (uint32_t)(r * (size_t)(16 * S::kT) + blk), w);
+        else chacha_block<ROUNDS>(k, r * (size_t)(16 * S::kT) + blk, w);
         uint32_t suspect = 0;
 #pragma unroll
         for (int cb = 0; cb < 4; cb++) {
@@ -623,7 +634,8 @@ template <int K, int T, int N, int ROUNDS>
 __global__ void __launch_bounds__(CTA)
 packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, size_t P,
                                const ChaChaKey *__restrict__ keys, const uint4 *__restrict__ b_image,
-                               const int64_t *acc_in, int64_t *out, unsigned *flag, int bulk_ok) {   // acc_in may equal out
+                               const int64_t *acc_in, int64_t *out, unsigned *flag, int bulk_ok,   // acc_in may equal out
+                               const ChaChaPre *__restrict__ pres) {
     typedef FusedShape<K, T, N> F;
     typedef Shape<K, T, N> S;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -669,13 +681,13 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
         } else {
             fill_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, tid, sIn);
         }
-        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, pres, warp, blockIdx.x, warp, lane, sD, flag);
     }
 #else
     uint4 s[F::GP][S::SC];
     if (blockIdx.x < ranges) {
         load_secrets_fused<F, K>(secrets, ld, dim, P, 0, ((size_t)blockIdx.x * CTA + tid) * K, s);
-        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, warp, blockIdx.x, warp, lane, sD, flag);
+        if ((size_t)warp < P) stage_draws_fused<F, ROUNDS>(keys, pres, warp, blockIdx.x, warp, lane, sD, flag);
     }
 #endif
 
@@ -770,7 +782,7 @@ packed_share_combine_tc_kernel(const int64_t *__restrict__ secrets, size_t ld, s
 #else
                     load_secrets_fused<F, K>(secrets, ld, dim, P, pg, (rn * CTA + tid) * K, s);     // consumed after the keystream
 #endif
-                    if (pg + warp < P) stage_draws_fused<F, ROUNDS>(keys, pg + warp, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
+                    if (pg + warp < P) stage_draws_fused<F, ROUNDS>(keys, pres, pg + warp, rn, warp, lane, sD + (buf ^ 1) * F::D_BYTES, flag);
                 }
             }
             mbar_wait(full_bar, parity);                   // rows consumed: the next pass may overwrite the secrets
@@ -878,7 +890,7 @@ cudaError_t dispatch(const LaunchCtx &lc, const GenericField &gf, int rounds, co
 
 template <int K, int T, int N, int ROUNDS>
 cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                         const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
+                         const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag, uint32_t *d_pre) {
     typedef FusedShape<K, T, N> F;
     const size_t B = (dim + K - 1) / K;
     const size_t ranges = (B + CTA - 1) / CTA;
@@ -892,18 +904,29 @@ cudaError_t launch_fused(const LaunchCtx &lc, const int64_t *secrets, size_t ld,
     const int per_sm = resident_ctas(regs, CTA, smem, static_smem, F::TMEM_COLS);
     const size_t grid = std::min<size_t>(ranges, (size_t)lc.sm_count * per_sm);
     const int bulk_ok = SDA_TC_BULK_IN && reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
+    // first-round constants per participant (d_pre: P ChaChaPre) when a participant's keystream stays below 2^32 blocks
+    ChaChaPre *pres = nullptr;
+#ifdef SDA_TC_FUSED_NO_PRE
+    d_pre = nullptr;
+#endif
+    if (d_pre != nullptr && P > 0 && ((B * (size_t)T + 7) / 8 + 16 * (size_t)T) >> 32 == 0) {
+        pres = reinterpret_cast<ChaChaPre *>(d_pre);
+        chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
+        ++*lc.nlaunch;
+    }
     kern<<<(unsigned)grid, CTA, smem, lc.stream>>>(secrets, ld, dim, B, P, keys, reinterpret_cast<const uint4 *>(d_b_image),
-                                                   acc_in, out, flag, bulk_ok);
+                                                   acc_in, out, flag, bulk_ok, pres);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
 
 template <int K, int T, int N>
 cudaError_t dispatch_fused(const LaunchCtx &lc, int rounds, const int64_t *secrets, size_t ld, size_t P, size_t dim,
-                           const ChaChaKey *keys, const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
-    if (rounds == 8) return launch_fused<K, T, N, 8>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
-    if (rounds == 12) return launch_fused<K, T, N, 12>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
-    return launch_fused<K, T, N, 20>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);
+                           const ChaChaKey *keys, const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag,
+                           uint32_t *d_pre) {
+    if (rounds == 8) return launch_fused<K, T, N, 8>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag, d_pre);
+    if (rounds == 12) return launch_fused<K, T, N, 12>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag, d_pre);
+    return launch_fused<K, T, N, 20>(lc, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag, d_pre);
 }
 
 #define SDA_TC_SHAPES(X) X(3, 2, 5) X(5, 4, 9) X(3, 4, 7) X(3, 4, 8)
@@ -954,11 +977,11 @@ cudaError_t launch_packed_share_tc(const LaunchCtx &lc, const FieldParams &f, co
 // fused share generation + clerk accumulation over the participants: out[n][B] = acc_in + sum_p shares(p)
 cudaError_t launch_packed_share_combine_tc(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, const uint8_t *d_b_image,
-                                           const int64_t *acc_in, int64_t *out, unsigned *flag) {
+                                           const int64_t *acc_in, int64_t *out, unsigned *flag, uint32_t *d_key_scratch) {
 #define X(K, T, N)                                                                                              \
     if (k == K && t == T && n == N) {                                                                           \
         *lc.kernel_name = "packed_share_combine<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8, TMEM-accumulated"; \
-        return dispatch_fused<K, T, N>(lc, rounds, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag);    \
+        return dispatch_fused<K, T, N>(lc, rounds, secrets, ld, P, dim, keys, d_b_image, acc_in, out, flag, d_key_scratch); \
     }
     SDA_TC_SHAPES(X)
 #undef X

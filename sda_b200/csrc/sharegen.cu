@@ -15,6 +15,7 @@
 // gen_range's rejection (probability ~2^-60 for the supported moduli) shifts the whole
 // stream, so a rejected word raises `flag` and the host redoes the call on the exact path
 // (draws pre-computed by draw_exact into scratch, kernels instantiated with FROM_MEM).
+#include "chacha_pre.cuh"
 #include "kernels.h"
 #include "vecio.cuh"
 
@@ -40,6 +41,21 @@ __device__ __forceinline__ ChaChaKey load_key(const ChaChaKey *keys, size_t p) {
     return k;
 }
 
+// the 8 u64 draws of block `block` (< 2^32) of a key whose first-round constants were precomputed (chacha_pre.cuh)
+template <int ROUNDS>
+__device__ __forceinline__ void chacha_words_pre(const ChaChaKey &key, const ChaChaPre &pre, uint32_t block, uint32_t (&w)[16]) {
+    chacha_block2<ROUNDS>(key.w, pre.w, block, w);
+}
+__device__ __forceinline__ ChaChaPre load_pre(const ChaChaPre *pres, size_t p) {
+    ChaChaPre r;
+    const uint4 *src = reinterpret_cast<const uint4 *>(pres + p);
+    const uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+    r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+    r.w[8] = c.x; r.w[9] = c.y; r.w[10] = c.z; r.w[11] = c.w;
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------
 // additive split, D = n - 1 draws per element, in-kernel randomness
 // ------------------------------------------------------------------------------------------
@@ -47,7 +63,7 @@ template <bool M61, uint32_t DK, int ROUNDS, int D>
 __global__ void __launch_bounds__(CTA)
 additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, const ChaChaKey *__restrict__ keys,
                       int64_t *__restrict__ out, FieldParams f, DrawParams dr, int in_lanes, int out_lanes,
-                      unsigned *flag) {
+                      unsigned *flag, const ChaChaPre *__restrict__ pres = nullptr) {
     constexpr int G = Unit<D>::G, NB = Unit<D>::NB;
     const size_t p = blockIdx.y;
     const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
@@ -55,6 +71,19 @@ additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim
     if (e0 >= dim) return;
     const int nvalid = (int)min((size_t)G, dim - e0);
     const ChaChaKey key = load_key(keys, p);
+    // pres != nullptr (Mersenne path, every block counter below 2^32): the participant's first-round constants
+    ChaChaPre pre{};
+    if (M61 && pres != nullptr) pre = load_pre(pres, p);
+    auto next_block = [&](size_t b, uint64_t (&dst)[8]) {
+        if (M61 && pres != nullptr) {
+            uint32_t w[16];
+            chacha_words_pre<ROUNDS>(key, pre, (uint32_t)b, w);
+#pragma unroll
+            for (int i = 0; i < 8; i++) dst[i] = ((uint64_t)w[2 * i] << 32) | w[2 * i + 1];
+        } else {
+            chacha_draws8<ROUNDS>(key, b, dst);
+        }
+    };
 
     int64_t x[G];
     load_run<G>(secrets + p * ld + e0, x, nvalid, in_lanes);
@@ -77,7 +106,7 @@ additive_split_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim
 #pragma unroll
             for (int j = 0; j < D; j++) {
                 const int q = e * D + j;
-                if (q % 8 == 0) chacha_draws8<ROUNDS>(key, u * NB + q / 8, blk);
+                if (q % 8 == 0) next_block(u * NB + q / 8, blk);
                 const uint64_t v = blk[q % 8];
                 const uint32_t w0 = (uint32_t)(v >> 32), hi = w0 & LOW29;
                 uint64_t s = (((uint64_t)hi << 32) | (uint32_t)v) + (w0 >> 29);
@@ -186,7 +215,8 @@ template <bool M61, uint32_t DK, int ROUNDS, bool FROM_MEM, bool FLOAT_IN = fals
 __global__ void __launch_bounds__(CTA)
 mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, const uint64_t *__restrict__ draws,
             int64_t *__restrict__ mask_out, int64_t *__restrict__ masked_out, FieldParams f, DrawParams dr,
-            int lanes, unsigned *flag, const float *__restrict__ fx = nullptr, double scale = 1.0) {
+            int lanes, unsigned *flag, const float *__restrict__ fx = nullptr, double scale = 1.0, ChaChaPre pre = ChaChaPre{},
+            int use_pre = 0) {
     constexpr int G = 8;
     const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
     const size_t e0 = u * G;
@@ -213,6 +243,11 @@ mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, cons
     if (FROM_MEM) {
 #pragma unroll
         for (int e = 0; e < G; e++) blk[e] = e < nvalid ? draws[e0 + e] : 0;
+    } else if (use_pre) {                        // every block counter below 2^32: first-round constants from the host
+        uint32_t w[16];
+        chacha_words_pre<ROUNDS>(key, pre, (uint32_t)u, w);
+#pragma unroll
+        for (int e = 0; e < 8; e++) blk[e] = ((uint64_t)w[2 * e] << 32) | w[2 * e + 1];
     } else {
         chacha_draws8<ROUNDS>(key, u, blk);
     }
@@ -273,7 +308,7 @@ template <bool M61, uint32_t DK>
 __global__ void __launch_bounds__(CTA)
 chacha_mask_combine_kernel(const ChaChaKey *__restrict__ keys, size_t P, size_t seeds_per_slice, size_t dim,
                            int64_t *__restrict__ out, size_t out_ld, FieldParams f, DrawParams dr, int lanes,
-                           unsigned *flag) {
+                           unsigned *flag, const ChaChaPre *__restrict__ pres = nullptr) {
     constexpr int G = 8;
     const size_t u = (size_t)blockIdx.x * CTA + threadIdx.x;
     const size_t e0 = u * G;
@@ -285,7 +320,43 @@ chacha_mask_combine_kernel(const ChaChaKey *__restrict__ keys, size_t P, size_t 
 #pragma unroll
     for (int e = 0; e < G; e++) acc[e] = 0;
     bool rej = false;
-    for (size_t p = p0; p < p1; p++) {
+    if constexpr (M61 && DK == DRAW_M61) {
+        if (pres != nullptr) {
+            // 2^61 - 1 with precomputed first-round constants (the launcher passes them when every block counter is below
+            // 2^32): a draw is (v & p) + (v >> 61) <= p + 7 with no compare, summed as it is and folded every 7 seeds; a
+            // rejected word (v >= 2^64 - 8: high word all ones) is looked for only when the block's largest high word says so
+            constexpr uint32_t LOW29 = 0x1fffffffu;
+            uint32_t since_fold = 0;
+            for (size_t p = p0; p < p1; p++) {
+                const ChaChaKey key = load_key(keys, p);
+                const ChaChaPre pre = load_pre(pres, p);
+                uint32_t w[16];
+                chacha_words_pre<20>(key, pre, (uint32_t)u, w);
+                uint32_t top = 0;
+#pragma unroll
+                for (int e = 0; e < G; e++) {
+                    top = max(top, w[2 * e]);
+                    acc[e] += (((uint64_t)(w[2 * e] & LOW29) << 32) | w[2 * e + 1]) + (w[2 * e] >> 29);
+                }
+                if (top == 0xffffffffu) {
+#pragma unroll
+                    for (int e = 0; e < G; e++) rej |= e < nvalid && w[2 * e] == 0xffffffffu && w[2 * e + 1] >= 0xfffffff8u;
+                }
+                if (++since_fold == 7) {
+                    since_fold = 0;
+#pragma unroll
+                    for (int e = 0; e < G; e++) acc[e] = (acc[e] & P61) + (acc[e] >> 61);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < G; e++) {
+                uint64_t a = (acc[e] & P61) + (acc[e] >> 61);
+                a = (a & P61) + (a >> 61);
+                acc[e] = a >= P61 ? a - P61 : a;
+            }
+        }
+    }
+    for (size_t p = (M61 && DK == DRAW_M61 && pres != nullptr) ? p1 : p0; p < p1; p++) {
         const ChaChaKey key = load_key(keys, p);
         uint64_t blk[8];
         chacha_draws8<20>(key, u, blk);
@@ -460,14 +531,21 @@ cudaError_t packed_dispatch(const LaunchCtx &lc, const FieldParams &f, const Dra
 
 template <bool M61, uint32_t DK, int ROUNDS, int D>
 cudaError_t additive_launch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, const int64_t *secrets,
-                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, int64_t *out, unsigned *flag) {
+                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, int64_t *out, unsigned *flag,
+                            uint32_t *d_pre) {
     constexpr int G = Unit<D>::G;
     const size_t units = (dim + G - 1) / G;
     dim3 grid((unsigned)((units + CTA - 1) / CTA), (unsigned)P);
     const int in_lanes = pick_lanes(secrets, ld, G);
     const int out_lanes = pick_lanes(out, dim, G);
+    ChaChaPre *pres = nullptr;
+    if (M61 && d_pre != nullptr && (((dim * (size_t)D + 7) / 8 + 8) >> 32) == 0) {
+        pres = reinterpret_cast<ChaChaPre *>(d_pre);
+        chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
+        ++*lc.nlaunch;
+    }
     additive_split_kernel<M61, DK, ROUNDS, D><<<grid, CTA, 0, lc.stream>>>(secrets, ld, dim, keys, out, f, dr,
-                                                                            in_lanes, out_lanes, flag);
+                                                                            in_lanes, out_lanes, flag, pres);
     ++*lc.nlaunch;
     return cudaGetLastError();
 }
@@ -475,8 +553,8 @@ cudaError_t additive_launch(const LaunchCtx &lc, const FieldParams &f, const Dra
 template <int D>
 cudaError_t additive_dispatch(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds,
                               const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                              int64_t *out, unsigned *flag) {
-#define SDA_AL(M61, DK, R) return additive_launch<M61, DK, R, D>(lc, f, dr, secrets, ld, P, dim, keys, out, flag)
+                              int64_t *out, unsigned *flag, uint32_t *d_pre) {
+#define SDA_AL(M61, DK, R) return additive_launch<M61, DK, R, D>(lc, f, dr, secrets, ld, P, dim, keys, out, flag, d_pre)
     if (f.kind == FIELD_MERSENNE61) {
         if (rounds == 8) SDA_AL(true, DRAW_M61, 8);
         if (rounds == 12) SDA_AL(true, DRAW_M61, 12);
@@ -509,17 +587,17 @@ bool additive_split_has_fast_path(int n) { return n >= 2; }   // n <= 5: unrolle
 
 cudaError_t launch_additive_split(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr, int rounds, int n,
                                   const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
-                                  const uint64_t *draws, int64_t *shares_out, unsigned *flag) {
+                                  const uint64_t *draws, int64_t *shares_out, unsigned *flag, uint32_t *d_key_scratch) {
     if (dim == 0 || P == 0) return cudaSuccess;
     if (P > 65535) return cudaErrorInvalidValue;
     if (draws == nullptr && n >= 2 && n <= 5) {
         *lc.kernel_name = f.kind == FIELD_MERSENNE61 ? "additive_split<in-kernel rng>/mersenne61"
                                                      : "additive_split<in-kernel rng>/generic";
         switch (n - 1) {
-        case 1: return additive_dispatch<1>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
-        case 2: return additive_dispatch<2>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
-        case 3: return additive_dispatch<3>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
-        case 4: return additive_dispatch<4>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag);
+        case 1: return additive_dispatch<1>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag, d_key_scratch);
+        case 2: return additive_dispatch<2>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag, d_key_scratch);
+        case 3: return additive_dispatch<3>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag, d_key_scratch);
+        case 4: return additive_dispatch<4>(lc, f, dr, rounds, secrets, ld, P, dim, keys, shares_out, flag, d_key_scratch);
         }
     }
     if (draws == nullptr && n > 5) {
@@ -558,12 +636,14 @@ cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawPar
     if (dim == 0) return cudaSuccess;
     const size_t units = (dim + 7) / 8;
     const unsigned grid = (unsigned)((units + CTA - 1) / CTA);
+    const ChaChaPre pre = chacha_prepare_host(key);
+    const int use_pre = (units >> 32) == 0;
     if (fx != nullptr) {                     // fused fixed-point encode + mask, in-kernel draws only
         if (draws != nullptr) return cudaErrorInvalidValue;
         const double scale = ldexp(1.0, frac_bits);
         int fl = pick_lanes(masked_out, 4, 8);
         if (mask_out && pick_lanes(mask_out, 4, 8) < fl) fl = pick_lanes(mask_out, 4, 8);
-#define SDA_MF(M61, DK, R) mask_kernel<M61, DK, R, false, true><<<grid, CTA, 0, lc.stream>>>(nullptr, dim, key, nullptr, mask_out, masked_out, f, dr, fl, flag, fx, scale)
+#define SDA_MF(M61, DK, R) mask_kernel<M61, DK, R, false, true><<<grid, CTA, 0, lc.stream>>>(nullptr, dim, key, nullptr, mask_out, masked_out, f, dr, fl, flag, fx, scale, pre, use_pre)
         if (f.kind == FIELD_MERSENNE61) {
             if (rounds == 8) SDA_MF(true, DRAW_M61, 8);
             else if (rounds == 12) SDA_MF(true, DRAW_M61, 12);
@@ -583,7 +663,7 @@ cudaError_t launch_mask(const LaunchCtx &lc, const FieldParams &f, const DrawPar
     if (l3 < lanes) lanes = l3;
 #define SDA_ML(M61, DK, R, MEM)                                                                               \
     mask_kernel<M61, DK, R, MEM><<<grid, CTA, 0, lc.stream>>>(secrets, dim, key, draws, mask_out, masked_out, f, \
-                                                              dr, lanes, flag)
+                                                              dr, lanes, flag, nullptr, 1.0, pre, use_pre)
     const bool m61 = f.kind == FIELD_MERSENNE61;
     if (draws != nullptr) {
         if (m61) SDA_ML(true, DRAW_M61, 20, true);
@@ -613,7 +693,8 @@ static size_t mask_combine_slices(int sm_count, size_t P, size_t dim) {
 }
 size_t chacha_mask_combine_scratch_elems(int sm_count, size_t P, size_t dim) {
     const size_t s = mask_combine_slices(sm_count, P, dim);
-    return s > 1 ? s * ((dim + 3) & ~(size_t)3) : 0;
+    // slice partials, then one ChaChaPre per seed (16-byte aligned: the partial rows are multiples of 4 elements)
+    return (s > 1 ? s * ((dim + 3) & ~(size_t)3) : 0) + (P * sizeof(ChaChaPre) + 7) / 8;
 }
 
 cudaError_t launch_chacha_mask_combine(const LaunchCtx &lc, const FieldParams &f, const DrawParams &dr,
@@ -628,10 +709,18 @@ cudaError_t launch_chacha_mask_combine(const LaunchCtx &lc, const FieldParams &f
     const size_t units = (dim + 7) / 8;
     dim3 grid((unsigned)((units + CTA - 1) / CTA), (unsigned)slices);
     const int lanes = pick_lanes(dst, dimp, 8);
-    if (f.kind == FIELD_MERSENNE61)
+    if (f.kind == FIELD_MERSENNE61) {
+        // first-round constants per seed behind the slice partials, when the scratch has room and the counters allow
+        const size_t used = slices > 1 ? slices * dimp : 0, need = (P * sizeof(ChaChaPre) + 7) / 8;
+        ChaChaPre *pres = nullptr;
+        if (scratch != nullptr && scratch_elems >= used + need && P > 0 && (units >> 32) == 0) {
+            pres = reinterpret_cast<ChaChaPre *>(scratch + used);
+            chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
+            ++*lc.nlaunch;
+        }
         chacha_mask_combine_kernel<true, DRAW_M61><<<grid, CTA, 0, lc.stream>>>(keys, P, sps, dim, dst, dimp, f, dr,
-                                                                                lanes, flag);
-    else
+                                                                                lanes, flag, pres);
+    } else
         chacha_mask_combine_kernel<false, DRAW_GENERIC><<<grid, CTA, 0, lc.stream>>>(keys, P, sps, dim, dst, dimp, f,
                                                                                      dr, lanes, flag);
     ++*lc.nlaunch;
