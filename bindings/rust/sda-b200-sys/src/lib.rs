@@ -119,6 +119,9 @@ pub mod ffi {
                                            m: usize, secrets_out: *mut i64, out_len: *mut usize) -> c_int;
         pub fn sda_mask(ctx: *mut SdaCtx, s: *const MaskingScheme, secrets: *const i64, dim: usize, rng_seed: *const u8,
                         mask_out: *mut i64, mask_len: *mut usize, masked_out: *mut i64) -> c_int;
+        pub fn sda_mask_share_generate(ctx: *mut SdaCtx, ms: *const MaskingScheme, ss: *const SharingScheme, secrets: *const i64,
+                                       dim: usize, mask_rng_seed: *const u8, share_rng_seed: *const u8, mask_out: *mut i64,
+                                       shares_out: *mut i64) -> c_int;
         pub fn sda_mask_combine(ctx: *mut SdaCtx, s: *const MaskingScheme, masks: *const i64, p: usize, mask_len: usize,
                                 out: *mut i64, out_len: *mut usize) -> c_int;
         pub fn sda_unmask(ctx: *mut SdaCtx, s: *const MaskingScheme, mask: *const i64, mask_len: usize,
@@ -205,6 +208,21 @@ impl Context {
             ffi::sda_share_generate(self.raw, s, secrets.as_ptr(), secrets.len(), rng_seed.as_ptr(), flat.as_mut_ptr())
         }));
         Ok((0..n).map(|r| flat[r * l..(r + 1) * l].to_vec()).collect())
+    }
+
+    /// `SecretMasker::mask` followed by `ShareGenerator::generate` on its output (participate.rs:53-54, :75-76) in one
+    /// call: `(mask, shares per clerk)`.  Same results as the two calls; the masked secrets stay on the device.
+    pub fn mask_share_generate(&self, ms: &MaskingScheme, ss: &SharingScheme, secrets: &[i64], mask_rng_seed: &[u8; 32],
+                               share_rng_seed: &[u8; 32]) -> Result<(Vec<i64>, Vec<Vec<i64>>)> {
+        let n = ss.output_size();
+        let l = ss.batches(secrets.len());
+        let mut mask = vec![0i64; ms.mask_len(secrets.len())];
+        let mut flat = vec![0i64; n * l];
+        try!(self.check(unsafe {
+            ffi::sda_mask_share_generate(self.raw, ms, ss, secrets.as_ptr(), secrets.len(), mask_rng_seed.as_ptr(),
+                                         share_rng_seed.as_ptr(), mask.as_mut_ptr(), flat.as_mut_ptr())
+        }));
+        Ok((mask, (0..n).map(|r| flat[r * l..(r + 1) * l].to_vec()).collect()))
     }
 
     /// Same into caller-provided (ideally pinned) storage `[n][l]`, row r = clerk r: no per-row allocation.
