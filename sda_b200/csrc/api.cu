@@ -566,6 +566,15 @@ int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const Field
     return fail(ctx, SDA_ERR_UNSUPPORTED, "no tensor-core kernel for this scheme");
 }
 
+// which generation of the fused share-gen -> clerk-sum kernel a shape runs on (measured, profiles/r02_kernels.md)
+bool fused_prefers_paired(const Packed &pk) {
+    static const char *force = getenv("SDA_B200_FUSED_KERNEL");      // "paired" / "v1": side-by-side measurements
+    if (force && force[0] == 'p') return true;
+    if (force && force[0] == 'v') return false;
+    (void)pk;
+    return true;
+}
+
 // ---- core device-side operations (shared by host and device entry points) --------------------
 
 int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t *d_secrets, size_t ld, size_t P,
@@ -1220,9 +1229,19 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
                 d_dst = (int64_t *)ctx->aux.p;
             }
             CU(ctx->keys_pre.reserve(packed_share_tc2_key_scratch_bytes(P)));
-            CU(launch_packed_share_combine_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
-                                              (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_acc_in,
-                                              d_dst, ctx->d_flag, (uint32_t *)ctx->keys_pre.p));
+            // the paired-tile generation of the fused kernel (packed_tc2f.cu) where it is the faster one; TENSOR_CORES_V1
+            // keeps the first (packed_tc.cu) for side-by-side runs
+            if (ctx->packed_path != SDA_PACKED_PATH_TENSOR_CORES_V1 && fused_prefers_paired(pk) &&
+                packed_share_combine_tc2_supported(pk.k, pk.t, pk.n, dim)) {
+                OK(ensure_image(ctx, TC_PAIRED, pk, M, &ctx->tc2_image, &ctx->tc2_image_key));
+                CU(launch_packed_share_combine_tc2(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
+                                                   (const ChaChaKey *)ctx->keys.p, (uint32_t *)ctx->keys_pre.p,
+                                                   (const uint8_t *)ctx->tc2_image.p, d_acc_in, d_dst, ctx->d_flag));
+            } else {
+                CU(launch_packed_share_combine_tc(ctx->lc(), ctx->rounds, pk.k, pk.t, pk.n, d_secrets, secrets_ld, P, dim,
+                                                  (const ChaChaKey *)ctx->keys.p, (const uint8_t *)ctx->tc_image.p, d_acc_in,
+                                                  d_dst, ctx->d_flag, (uint32_t *)ctx->keys_pre.p));
+            }
             unsigned rejected = 0;
             OK(read_flags(ctx, &rejected, nullptr));
             if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)

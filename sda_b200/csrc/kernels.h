@@ -110,6 +110,12 @@ size_t packed_share_tc2_key_scratch_bytes(size_t P);
 cudaError_t launch_packed_share_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets, size_t ld,
                                     size_t P, size_t dim, size_t first_batch, size_t n_batches, const ChaChaKey *keys,
                                     uint32_t *d_key_scratch, const uint8_t *d_b_image, int64_t *shares_out, unsigned *flag);
+// share generation fused with the clerk sums on the paired-tile machinery (packed_tc2f.cu): 2^61 - 1, the instantiated
+// shapes; operand images as packed_share_tc2_build_image, d_key_scratch as launch_packed_share_tc2
+bool packed_share_combine_tc2_supported(int k, int t, int n, size_t dim);
+cudaError_t launch_packed_share_combine_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
+                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, uint32_t *d_key_scratch,
+                                            const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag);
 // mask -> share generation in one kernel (packed_tc2m.cu): both schemes over 2^61 - 1, 20 rounds, the instantiated shapes.
 // mask_keys[P]: the key of every participant's mask stream; mask_out: [P][dim] (Full scheme) or nullptr;
 // d_key_scratch: twice packed_share_tc2_key_scratch_bytes(P).  Whole vectors only.

@@ -1,0 +1,267 @@
+// packed_tc2f.cu -- share generation fused with the clerk sums (participate.rs:75-76 + clerk.rs:71-86 on one box) on the
+// paired-tile machinery of packed_tc2.cuh: the second generation of packed_tc.cu's packed_share_combine_tc_kernel.
+//
+// A CTA owns one pass of batches (Shape2::PASS of them: one or two E/O tile pairs) and walks the participants: for each it
+// stages that participant's secrets and draws of the pass as operand tiles exactly as the share-generation kernel does and
+// multiplies them into the SAME TMEM accumulators (tcgen05.mma with accumulate).  No share is ever folded or stored per
+// participant: the limb sums keep growing (at most 8 (k + t) 255^2 per participant and limb, so 256 participants fit the
+// s32 accumulators), are drained every 256 participants and at the end -- composed with 64-bit arithmetic and added to the
+// running sums of the pass, which live in the output between drains.  Per participant a
+// thread's work is its share of the keystream (one block for t = 4), the staging of 2k secrets and one barrier: the kernel is
+// the keystream plus ~10 %.
+//
+// p = 2^61 - 1, the shapes BASELINE names, any round count.  Same rejection contract as the other kernels: a gen_range
+// rejection raises `flag` and the caller redoes the call on the materialising path.
+#include "packed_tc2.cuh"
+
+namespace sda {
+
+namespace {
+
+constexpr int MAX_ACCUM2 = 256;       // participants per TMEM accumulation (packed_tc.cu: 256 * 96 * 255^2 < 2^31)
+
+// limb sums d[s] < 2^31 at the limb plan's positions -> canonical value mod p (runs once per 256 participants)
+template <int W5>
+__device__ __forceinline__ uint64_t compose_wide2(const uint32_t (&d)[8]) {
+    // positions 0, 8, 16, 24 | 32 + (0, 8, 8 + W5, 16 + W5)
+    const uint64_t lo = (uint64_t)d[0] + ((uint64_t)d[1] << 8) + ((uint64_t)d[2] << 16) + ((uint64_t)d[3] << 24);   // < 2^56
+    const uint64_t hi = (uint64_t)d[4] + ((uint64_t)d[5] << 8) + ((uint64_t)d[6] << (8 + W5)) + ((uint64_t)d[7] << (16 + W5));   // < 2^56
+    // hi 2^32 = (hi mod 2^29) 2^32 + (hi >> 29) 2^61 == (hi mod 2^29) 2^32 + (hi >> 29)
+    uint64_t v = lo + ((hi & LOW29) << 32) + (hi >> 29);       // < 2^56 + 2^61 + 2^27
+    v = (v & P61) + (v >> 61);
+    return v >= P61 ? v - P61 : v;
+}
+
+// the NK MMAs of one tile; `fresh`: the first of them overwrites the accumulator
+template <class S>
+__device__ __forceinline__ void issue_tile_acc(uint32_t taddr, uint32_t d_tile, uint32_t s_tile, uint32_t b_img, bool fresh) {
+    const uint64_t dd = umma_desc(d_tile, S::SBO_D), ds = umma_desc(s_tile, S::SBO_S), db = umma_desc(b_img, S::SBO_B);
+#pragma unroll
+    for (int kk = 0; kk < S::NKD; kk++)
+        umma_i8(taddr, dd + ((2 * LBO * kk) >> 4), db + ((2 * LBO * kk) >> 4), S::IDESC, (kk > 0 || !fresh) ? 1u : 0u);
+#pragma unroll
+    for (int kk = 0; kk < S::NKS; kk++)
+        umma_i8(taddr, ds + ((2 * LBO * kk) >> 4), db + ((2 * LBO * (S::NKD + kk)) >> 4), S::IDESC, 1);
+}
+
+template <int K, int T, int N, int ROUNDS>
+__global__ void __launch_bounds__(CTA2, (512 / (2 * Shape2<K, T, N>::PAIRS * Shape2<K, T, N>::ACC_COLS)) < Shape2<K, T, N>::RESIDENT
+                                              ? (512 / (2 * Shape2<K, T, N>::PAIRS * Shape2<K, T, N>::ACC_COLS)) : Shape2<K, T, N>::RESIDENT)
+packed_share_combine_tc2_kernel(const int64_t *__restrict__ secrets, size_t ld, size_t dim, size_t B, uint32_t P,
+                                uint32_t units, uint32_t full_in_units,
+                                const ChaChaKey *__restrict__ keys, const ChaChaPre *__restrict__ pres,
+                                const uint4 *__restrict__ b_image, const int64_t *acc_in, int64_t *out,   // acc_in may equal out
+                                unsigned *flag, int bulk_ok) {
+    typedef Shape2<K, T, N> S;
+    constexpr int ACCS = 2 * S::PAIRS;                     // accumulators: E and O of every pair
+    constexpr int TCOLS = ACCS * S::ACC_COLS;
+    static_assert(TCOLS <= 512, "TMEM columns");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t *sD = smem;                                    // 2 x (PAIRS x {E, O} tiles x 128 rows x draws)
+    uint8_t *sS = smem + 2 * S::D_BYTES;                   // PAIRS x {E, O} tiles x 128 rows x secrets
+    uint8_t *sB = sS + S::S_BYTES;                         // the constant operand, E image then O image
+    int64_t *sIn = reinterpret_cast<int64_t *>(sB + 2 * S::B_IMG);   // the coming participant's raw secrets of the pass
+    __shared__ __align__(8) uint64_t mbar[2];              // [0] full (MMAs done), [1] secrets landed
+    __shared__ uint32_t tmem_base;
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(smem_u32(&tmem_base)), "n"(TCOLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&mbar[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (uint32_t i = tid; i < 2 * S::B_IMG / 16; i += CTA2) reinterpret_cast<uint4 *>(sB)[i] = __ldg(b_image + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = tmem_base;
+    const uint32_t my_taddr = taddr + ((uint32_t)(warp * 32) << 16);
+    const uint32_t full_bar = smem_u32(&mbar[0]), landed_bar = smem_u32(&mbar[1]);
+    const uint32_t d_base = smem_u32(sD), s_base = smem_u32(sS), b_base = smem_u32(sB), sin_addr = smem_u32(sIn);
+    uint32_t parity = 0, landed_parity = 0, buf = 0;
+
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const bool by_bulk = bulk_ok != 0 && u < full_in_units;     // the pass lies inside the vectors, sources 16-byte aligned
+        // this thread's batches: 2 tid and 2 tid + 1 of every pair.  The running sums live in `out` between drains (a drain
+        // every 256 participants: their traffic is nothing next to the keystream), the first drain starts from acc_in
+        const size_t pass_first = (size_t)u * S::PASS;
+        bool drained_before = false;
+        // participant 0 of the pass: secrets and draws
+        if (by_bulk) {
+            if (tid == 0) bulk_load_secrets2<S, K>(secrets, ld, 0, u, sin_addr, landed_bar);
+        } else {
+            fill_secrets2<S, K>(secrets, ld, dim, 0, u, tid, sIn);
+        }
+        stage_draws2<S, ROUNDS>(load_keys2(keys, pres, 0), u, tid, sD + buf * S::D_BYTES, flag);
+        uint32_t in_tmem = 0;
+        for (uint32_t p = 0; p < P; p++) {
+            const bool more = p + 1 < P;
+            KeyRegs knext;
+            if (more) knext = load_keys2(keys, pres, p + 1);
+            if (by_bulk) {
+                mbar_wait(landed_bar, landed_parity);
+                landed_parity ^= 1;
+            }
+            uint4 v[S::PAIRS][K];
+#pragma unroll
+            for (int q = 0; q < S::PAIRS; q++) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(sIn + (q * 256 + 2 * tid) * K);
+#pragma unroll
+                for (int i = 0; i < K; i++) v[q][i] = row[i];
+            }
+#pragma unroll
+            for (int q = 0; q < S::PAIRS; q++) {
+                uint32_t sign = 0;
+#pragma unroll
+                for (int i = 0; i < K; i++) sign |= v[q][i].y | v[q][i].w;
+                if ((int32_t)sign < 0) {
+#pragma unroll
+                    for (int i = 0; i < K; i++) {
+                        canon_pair2(v[q][i].x, v[q][i].y);
+                        canon_pair2(v[q][i].z, v[q][i].w);
+                    }
+                }
+                uint8_t *te = sS + (2 * q) * S::S_TILE + (tid >> 3) * S::SBO_S + (tid & 7) * 16;
+#pragma unroll
+                for (int c = 0; c < S::SC; c++) {
+                    *reinterpret_cast<uint4 *>(te + c * LBO) = v[q][c];                          // E: words 0 .. SC-1
+                    *reinterpret_cast<uint4 *>(te + S::S_TILE + c * LBO) = v[q][K - S::SC + c];  // O: words K-SC .. K-1
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_cur = d_base + buf * S::D_BYTES;
+            if (warp == 0) {
+                if (elect_one()) {
+#pragma unroll
+                    for (int q = 0; q < S::PAIRS; q++) {
+                        issue_tile_acc<S>(taddr + (2 * q) * S::ACC_COLS, d_cur + (2 * q) * S::D_TILE, s_base + (2 * q) * S::S_TILE, b_base,
+                                          in_tmem == 0);
+                        issue_tile_acc<S>(taddr + (2 * q + 1) * S::ACC_COLS, d_cur + (2 * q + 1) * S::D_TILE,
+                                          s_base + (2 * q + 1) * S::S_TILE, b_base + S::B_IMG, in_tmem == 0);
+                    }
+                    commit2(full_bar);
+                    // everyone is past the barrier, i.e. has read this participant's raw secrets: the next one's may land
+                    if (more && by_bulk) bulk_load_secrets2<S, K>(secrets, ld, p + 1, u, sin_addr, landed_bar);
+                }
+                __syncwarp();
+            }
+            in_tmem++;
+            // the next participant's keystream (and, off the bulk path, its secrets) under the MMAs
+            if (more) {
+                stage_draws2<S, ROUNDS>(knext, u, tid, sD + (buf ^ 1) * S::D_BYTES, flag);
+                if (!by_bulk) fill_secrets2<S, K>(secrets, ld, dim, p + 1, u, tid, sIn);
+            }
+            mbar_wait(full_bar, parity);               // tiles consumed: the next participant may overwrite the secrets
+            parity ^= 1;
+            buf ^= 1;
+            if (in_tmem == MAX_ACCUM2 || !more) {      // drain before the accumulators fill up, and at the end
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const int64_t *src = drained_before ? out : acc_in;
+#pragma unroll
+                for (int q = 0; q < S::PAIRS; q++)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const size_t b = pass_first + (size_t)(q * 256 + 2 * tid + h);
+                        uint32_t d[N][8];
+                        tmem_ld_shares<N>(my_taddr + (2 * q + h) * S::ACC_COLS, d);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (b < B) {
+#pragma unroll
+                            for (int j = 0; j < N; j++) {
+                                int64_t a = src != nullptr ? src[(size_t)j * B + b] : 0;
+                                if (a < 0) a = (int64_t)canon_negative(a);
+                                const uint64_t a0 = (uint64_t)a >= P61 ? (((uint64_t)a & P61) + ((uint64_t)a >> 61)) % P61 : (uint64_t)a;
+                                const uint64_t x = a0 + compose_wide2<S::W5>(d[j]);
+                                out[(size_t)j * B + b] = (int64_t)(x >= P61 ? x - P61 : x);
+                            }
+                        }
+                    }
+                drained_before = true;
+                in_tmem = 0;
+                // the next MMA (fresh accumulators) is issued after the next staging barrier, which every thread reaches
+                // only after these loads
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+        }
+        // sIn, sS and the draw buffers are reused by the next pass: every thread is past its reads (the last full wait),
+        // and the first staging barrier of the next pass orders the rest
+        __syncthreads();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(TCOLS) : "memory");
+}
+
+template <int K, int T, int N, int ROUNDS>
+cudaError_t launch_fused2(const LaunchCtx &lc, const int64_t *secrets, size_t ld, size_t P, size_t dim, const ChaChaKey *keys,
+                          uint32_t *d_pre, const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
+    typedef Shape2<K, T, N> S;
+    constexpr int TCOLS = 2 * S::PAIRS * S::ACC_COLS;
+    const size_t B = (dim + K - 1) / K;
+    const size_t units = (B + S::PASS - 1) / S::PASS;
+    if (units == 0 || P == 0) return cudaSuccess;
+    if (units >> 31 || P >> 31 || (B * (size_t)T + 7) / 8 >> 32) return cudaErrorInvalidValue;
+    auto kern = packed_share_combine_tc2_kernel<K, T, N, ROUNDS>;
+    const size_t smem = smem_capping_residency(S::SMEM, 512 / TCOLS);
+    static KernelSetup setup;
+    int regs = 0;
+    size_t static_smem = 0;
+    const cudaError_t se = setup_kernel(setup, kern, smem, &regs, &static_smem);
+    if (se != cudaSuccess) return se;
+    const int per_sm = resident_ctas(regs, CTA2, smem, static_smem, TCOLS);
+    const size_t grid = std::min<size_t>(units, (size_t)lc.sm_count * per_sm);
+    const int bulk_ok = reinterpret_cast<uintptr_t>(secrets) % 16 == 0 && (ld % 2 == 0 || P == 1);
+    const size_t full_in = dim / ((size_t)S::PASS * K);
+    ChaChaPre *pres = reinterpret_cast<ChaChaPre *>(d_pre);
+    chacha_prepare_kernel<<<(unsigned)((P + 127) / 128), 128, 0, lc.stream>>>(keys, P, pres);
+    ++*lc.nlaunch;
+    kern<<<(unsigned)grid, CTA2, smem, lc.stream>>>(secrets, ld, dim, B, (uint32_t)P, (uint32_t)units,
+                                                    (uint32_t)std::min<size_t>(full_in, 0xffffffffu),
+                                                    keys, pres,
+                                                    reinterpret_cast<const uint4 *>(d_b_image), acc_in, out, flag, bulk_ok);
+    ++*lc.nlaunch;
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+#define SDA_TC2F_SHAPES(X) X(3, 2, 5) X(5, 4, 9) X(3, 4, 7) X(3, 4, 8)
+
+bool packed_share_combine_tc2_supported(int k, int t, int n, size_t dim) {
+    const size_t B = (dim + (size_t)k - 1) / (size_t)k;
+    if ((B * (size_t)t + 7) / 8 >> 32) return false;
+#define X(K, T, N) if (k == K && t == T && n == N) return true;
+    SDA_TC2F_SHAPES(X)
+#undef X
+    return false;
+}
+
+// fused share generation + clerk accumulation over the participants: out[n][B] = acc_in + sum_p shares(p).
+// d_key_scratch: packed_share_tc2_key_scratch_bytes(P); d_b_image: packed_share_tc2_build_image's two images.
+cudaError_t launch_packed_share_combine_tc2(const LaunchCtx &lc, int rounds, int k, int t, int n, const int64_t *secrets,
+                                            size_t ld, size_t P, size_t dim, const ChaChaKey *keys, uint32_t *d_key_scratch,
+                                            const uint8_t *d_b_image, const int64_t *acc_in, int64_t *out, unsigned *flag) {
+#define X(K, T, N)                                                                                                        \
+    if (k == K && t == T && n == N) {                                                                                     \
+        *lc.kernel_name = "packed_share_combine<" #K "," #T "," #N ">/mersenne61 tcgen05.mma.kind::i8, paired tiles, TMEM-accumulated"; \
+        if (rounds == 8) return launch_fused2<K, T, N, 8>(lc, secrets, ld, P, dim, keys, d_key_scratch, d_b_image, acc_in, out, flag); \
+        if (rounds == 12) return launch_fused2<K, T, N, 12>(lc, secrets, ld, P, dim, keys, d_key_scratch, d_b_image, acc_in, out, flag); \
+        return launch_fused2<K, T, N, 20>(lc, secrets, ld, P, dim, keys, d_key_scratch, d_b_image, acc_in, out, flag);   \
+    }
+    SDA_TC2F_SHAPES(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sda

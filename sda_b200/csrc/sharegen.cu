@@ -233,8 +233,21 @@ mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, cons
 #pragma unroll
             for (int e = 0; e < G; e++) v[e] = e < nvalid ? __ldg(fx + e0 + e) : 0.f;
         }
+        if constexpr (M61) {
+            // x 2^frac_bits is exact in float (a power-of-two scale; overflow saturates the conversion exactly as the
+            // double product would), and |q| < 2^60 -- every realistic update -- needs one masked add to become a residue
+            const float sf = (float)scale;
 #pragma unroll
-        for (int e = 0; e < G; e++) x[e] = (int64_t)canon<M61>(f, __double2ll_rn((double)v[e] * scale));
+            for (int e = 0; e < G; e++) {
+                const long long q = __float2ll_rn(v[e] * sf);
+                uint64_t r = (uint64_t)q + (P61 & (uint64_t)(q >> 63));
+                if (((uint64_t)q + (1ull << 60)) >> 61) r = canon<true>(f, (int64_t)q);          // |q| >= 2^60: the general way
+                x[e] = (int64_t)r;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < G; e++) x[e] = (int64_t)canon<M61>(f, __double2ll_rn((double)v[e] * scale));
+        }
     } else {
         load_run<G>(secrets + e0, x, nvalid, lanes);
     }

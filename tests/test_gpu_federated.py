@@ -124,6 +124,23 @@ def test_fused_encode_mask_equals_encode_then_mask(ctx, oracle, modulus):
             assert np.array_equal(d_masked.cpu().numpy(), util.canon(oracle, modulus, emasked)), (dim, modulus, ms)
             assert d_mask.cpu().numpy()[:nmask].tolist() == util.canon(oracle, modulus, emask).tolist() if nmask and ms.c.kind == 1 \
                 else d_mask.cpu().numpy()[:nmask].tolist() == list(emask)
+    # extreme inputs (around |q| = 2^60, 2^61, 2^63, infinities, NaN, denormals, -0.0): the fused pass encodes exactly as
+    # sda_fixed_encode_dev does (the fast float path and its general branch)
+    if modulus == P61:
+        xe = np.array([2.0 ** 43, -2.0 ** 43, 2.0 ** 44, -2.0 ** 44, 2.0 ** 44 - 2.0 ** 21, 2.0 ** 45, -2.0 ** 45, 2.0 ** 46, 2.0 ** 47,
+                       -2.0 ** 47, 1e30, -1e30, np.inf, -np.inf, np.nan, 1e-45, -1e-45, -0.0, 0.0, 3.4e38, -3.4e38, 0.5 * 2.0 ** -16,
+                       1.5 * 2.0 ** -16, 2.5 * 2.0 ** -16, -0.5 * 2.0 ** -16], dtype=np.float32)
+        d_xe = t.from_numpy(xe).cuda()
+        d_q = t.empty(len(xe), dtype=t.int64, device="cuda")
+        ctx.fixed_encode_dev(P61, FRAC, d_xe, len(xe), d_q)
+        for ms in (LMS.None_(), LMS.Full(P61)):
+            seed = util.seed_bytes("fusedmask/extreme")
+            d_m1, d_o1 = t.zeros(len(xe), dtype=t.int64, device="cuda"), t.empty(len(xe), dtype=t.int64, device="cuda")
+            d_m2, d_o2 = t.zeros(len(xe), dtype=t.int64, device="cuda"), t.empty(len(xe), dtype=t.int64, device="cuda")
+            ctx.fixed_encode_mask_dev(ms, P61, FRAC, d_xe, len(xe), seed, d_m1, d_o1)
+            ctx.mask_dev(ms, d_q, len(xe), seed, d_m2, d_o2)
+            ctx.synchronize()
+            assert t.equal(d_o1, d_o2) and t.equal(d_m1, d_m2), (ms.c.kind, d_o1.cpu().numpy(), d_o2.cpu().numpy())
     # an unaligned float vector takes the scalar loads
     x = rng.standard_normal(1001).astype(np.float32)
     d_x = t.from_numpy(x).cuda()
