@@ -566,11 +566,9 @@ int launch_share_tc(sda_ctx *ctx, const Packed &pk, const Matrix &M, const Field
     return fail(ctx, SDA_ERR_UNSUPPORTED, "no tensor-core kernel for this scheme");
 }
 
-// which generation of the fused share-gen -> clerk-sum kernel a shape runs on (measured, profiles/r02_kernels.md)
+// which generation of the fused share-gen -> clerk-sum kernel a shape runs on: the paired-tile one is faster on every
+// instantiated shape (profiles/r02_kernels.md: 6 / 15 / 17 % on configs #3 / #4 / #5)
 bool fused_prefers_paired(const Packed &pk) {
-    static const char *force = getenv("SDA_B200_FUSED_KERNEL");      // "paired" / "v1": side-by-side measurements
-    if (force && force[0] == 'p') return true;
-    if (force && force[0] == 'v') return false;
     (void)pk;
     return true;
 }

@@ -115,6 +115,15 @@ def main():
                        lambda: ctx.share_generate_dev(s, sec, dim, P, dim, sd, sh), P * dim, P * (dim + n * B) * 8,
                        f"8(1+n/k) = {8 * (1 + n / s.input_size()):.2f} B per secret")
             ctx.set_packed_path(0)
+            # share generation fused with the clerk sums (TMEM-accumulated over the participants): both generations
+            accs = empty(n, B)
+            for path, label in ((0, "paired tiles"), (3, "first generation")):
+                ctx.set_packed_path(path)
+                timeit(f"share_generate_combine {name} [{P}][10M] ({label})",
+                       lambda: ctx.share_generate_combine_dev(s, sec, dim, P, dim, sd, accs), P * dim, (P * dim + n * B) * 8,
+                       "reads 8 B per secret, writes the n clerk sums once")
+            ctx.set_packed_path(0)
+            del accs
             if "cfg3" in name or "cfg5" in name:
                 # the participant's two steps (participate.rs:53-54, :75-76): Full mask then share generation, as two
                 # entry points (P mask calls, masked secrets through HBM) and as the one fused kernel
