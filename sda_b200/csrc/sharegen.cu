@@ -278,9 +278,9 @@ mask_kernel(const int64_t *__restrict__ secrets, size_t dim, ChaChaKey key, cons
             const uint64_t sd = (((uint64_t)hi << 32) | (uint32_t)v) + (w0 >> 29);
             suspect = max(suspect, hi);
             wide |= (uint32_t)((uint64_t)x[e] >> 61);
-            const uint64_t t = (uint64_t)x[e] + sd;                    // < 2^62 when the secret is below 2^61
-            uint64_t r = (t & P61) + (t >> 61);                         // <= p
-            r = r >= P61 ? r - P61 : r;
+            // secret <= p (below 2^61) and, off the suspect path, sd < p: the sum is below 2 p, one conditional subtraction
+            const uint64_t t = (uint64_t)x[e] + sd;
+            const uint64_t r = t >= P61 ? t - P61 : t;
             mk[e] = (int64_t)sd;                                        // full.rs:24-27
             md[e] = (int64_t)r;                                         // full.rs:28-31
         }
