@@ -26,6 +26,20 @@ seeds = b"".join(hashlib.sha256(b"%d" % i).digest() for i in range(P))
 ctx.share_generate_dev(s, sec, dim, P, dim, seeds, out); ctx.synchronize()
 PY
 done
+# the fused share-gen -> clerk-sum kernel (paired tiles) on config #5's shape, 256 participants x 10M
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:packed_share_combine_tc2 -c 1 -o gpurun_out/r02_fused2 -f \
+  python - > gpurun_out/r02_ncu_fused2.log 2>&1 <<'PY'
+import hashlib, torch, sda_b200
+from sda_b200 import params
+ctx = sda_b200.Context(0)
+s = params.config5()
+P, dim = 256, 10_000_000
+sec = torch.empty((P, dim), dtype=torch.int64, device="cuda"); ctx.synth_fill_dev(3, params.P61, 0, P * dim, sec)
+out = torch.empty((s.output_size(), s.batches(dim)), dtype=torch.int64, device="cuda")
+seeds = b"".join(hashlib.sha256(b"%d" % i).digest() for i in range(P))
+ctx.share_generate_combine_dev(s, sec, dim, P, dim, seeds, out); ctx.synchronize()
+print(ctx.last_kernel())
+PY
 # reveal (config #4's 9 x [2M] and 7 clerks x [3.33M]) and the varint codec
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:reveal_tc -s 6 -c 2 -o gpurun_out/r02_reveal -f \
   python tools/kernel_bench.py --only packed_reconstruct > gpurun_out/r02_ncu_reveal.log 2>&1
