@@ -539,3 +539,54 @@ def test_mask_share_generate_redo_after_rejection(oracle, torch_cuda, monkeypatc
     assert np.array_equal(res[0][1][1], util.canon(oracle, ss.modulus, exp))
     plain.close()
     forced.close()
+
+
+@pytest.mark.parametrize("mk", [params.config3, params.config5], ids=["cfg3", "cfg5"])
+@pytest.mark.parametrize("mask_kind", ["full", "chacha"])
+def test_masked_pipeline_reveals_the_sum(ctx, oracle, torch_cuda, mk, mask_kind):
+    """participant -> clerks -> recipient at a size the oracle does not finish in seconds, through the fused kernels:
+    mask + share in one kernel for 12 participants x 1M secrets, per-clerk sums, reveal from a clerk subset, mask
+    combine, unmask == the column sums of the secrets; the same clerk sums from the share-gen -> clerk-sum kernel fed
+    with the masked secrets (the two fused paths agree with each other and with the unfused arithmetic)"""
+    t = torch_cuda
+    ss = mk()
+    p, n, k, need = ss.modulus, ss.output_size(), ss.input_size(), ss.c.secret_count + ss.c.privacy_threshold
+    P, dim = 12, 1_000_003
+    B = ss.batches(dim)
+    ms = LMS.Full(p) if mask_kind == "full" else LMS.ChaCha(p, dim, 128)
+    mask_len = dim if mask_kind == "full" else 4
+    d_sec = t.empty((P, dim), dtype=t.int64, device="cuda")
+    ctx.synth_fill_dev(21, p, 0, P * dim, d_sec)
+    mseeds = b"".join(util.seed_bytes(f"pl/m/{pi}") for pi in range(P))
+    sseeds = b"".join(util.seed_bytes(f"pl/s/{pi}") for pi in range(P))
+    d_masks = t.empty((P, mask_len), dtype=t.int64, device="cuda")
+    d_shares = t.empty((P, n, B), dtype=t.int64, device="cuda")
+    ctx.mask_share_generate_dev(ms, ss, d_sec, dim, P, dim, mseeds, sseeds, d_masks, d_shares)
+    assert "mask+packed_share" in ctx.last_kernel()
+    d_sum = t.empty((n, B), dtype=t.int64, device="cuda")
+    for c in range(n):
+        ctx.share_combine_dev(ss, d_shares[:, c, :], n * B, P, B, d_sum[c])
+    # the unfused mask, then the fused share-gen -> clerk-sum kernel on the masked secrets: the same clerk sums
+    d_masked = t.empty((P, dim), dtype=t.int64, device="cuda")
+    d_m2 = t.empty((P, mask_len), dtype=t.int64, device="cuda")
+    for pi in range(P):
+        ctx.mask_dev(ms, d_sec[pi], dim, mseeds[32 * pi:32 * pi + 32], d_m2[pi], d_masked[pi])
+    assert t.equal(d_m2, d_masks)
+    d_sum2 = t.empty((n, B), dtype=t.int64, device="cuda")
+    ctx.share_generate_combine_dev(ss, d_masked, dim, P, dim, sseeds, d_sum2)
+    assert "paired tiles, TMEM-accumulated" in ctx.last_kernel()
+    ctx.synchronize()
+    assert t.equal(d_sum, d_sum2)
+    # recipient: reveal from a subset of the clerks, combine the masks, unmask
+    idx = sorted(np.random.default_rng(3).permutation(n)[:need + (need < n)].tolist())
+    d_sub = d_sum[idx].contiguous()
+    d_rec = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.secret_reconstruct_dev(ss, dim, idx, d_sub, B, len(idx), B, d_rec)
+    d_mask_total = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.mask_combine_dev(ms, d_masks, P, mask_len, d_mask_total)
+    d_out = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.unmask_dev(ms, d_mask_total, d_rec, dim, d_out)
+    d_tot = t.empty(dim, dtype=t.int64, device="cuda")
+    ctx.share_combine_dev(LSS.Additive(2, p), d_sec, dim, P, dim, d_tot)
+    ctx.synchronize()
+    assert t.equal(d_out, d_tot)
