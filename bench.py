@@ -839,7 +839,7 @@ def main():
     ap.add_argument("--e2e-participants", type=int, default=4)
     ap.add_argument("--e2e-mode", default="pipelined", choices=["pipelined", "phases"],
                     help="host-buffer leg: clerks of round i-1 concurrently with the participants of round i, or one after the other")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="client threads (one context each) of the host-buffer leg")
+    ap.add_argument("--e2e-threads", type=int, default=6, help="client threads (one context each) of the host-buffer leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
