@@ -41,7 +41,8 @@ constexpr int SDA_TC2_MAX_GROUPS = 4;  // run-time share count: up to 4 groups o
 
 constexpr int gcd_k(int a, int b) { return b == 0 ? a : gcd_k(b, a % b); }
 
-template <int K, int T, int N>
+// FORCE_PAIRS: 0 = the choice below; the fused share-gen -> clerk-sum kernel forces one pair per pass (packed_tc2f.cu)
+template <int K, int T, int N, int FORCE_PAIRS = 0>
 struct Shape2 {
     static_assert(T >= 1, "at least one draw per batch");
     static constexpr int TT = T;
@@ -61,7 +62,7 @@ struct Shape2 {
     // two pairs per pass give every thread whole keystream blocks when t is not a multiple of 4 -- where four CTAs
     // still fit an SM with them (56960 bytes each after the per-CTA reserve); otherwise one pair, and the warps of a CTA
     // share the pass's 32 t blocks unevenly
-    static constexpr int PAIRS = T % 4 != 0 && smem_for(2) <= 56960 ? 2 : 1;
+    static constexpr int PAIRS = FORCE_PAIRS ? FORCE_PAIRS : (T % 4 != 0 && smem_for(2) <= 56960 ? 2 : 1);
     static constexpr int PASS = PAIRS * 256;                 // batches per pass
     static constexpr int NBLK = PASS * T / 8;                // keystream blocks per pass (8 draws each), a multiple of 32
     static constexpr int NB = (NBLK + CTA2 - 1) / CTA2;      // ... per thread; odd t leaves the last round to warps 0 and 1
