@@ -31,4 +31,11 @@ timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pyt
   -k "mask_share_generate_matches and cfg3 and full" > gpurun_out/sanitize_racecheck_masked.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_masked.log
 timeout 1500 compute-sanitizer --tool synccheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
   -k "mask_share_generate_matches and cfg5 and full" > gpurun_out/sanitize_synccheck_masked.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_synccheck_masked.log
+# the paired-tile share-gen -> clerk-sum kernel (TMEM accumulation over participants, drains, two participants per step), the
+# keystream-constant variants of the mask / mask-combine / additive kernels
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py tests/test_gpu_parity.py -q -m gpu \
+  -k "share_generate_combine or tmem_accumulation or (chacha_mask and 2305843009213693951) or (additive_generate and 3-2305843009213693951)" \
+  > gpurun_out/sanitize_memcheck_fused2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_fused2.log
+timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
+  -k "share_generate_combine or (tmem_accumulation and cfg3)" > gpurun_out/sanitize_racecheck_fused2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_fused2.log
 (echo "compute-sanitizer on a B200 (tools/gpu_sanitize.sh), round 2"; for f in gpurun_out/sanitize_*.log; do echo "== $(basename $f)"; grep -v "^$" $f | tail -6; done) > gpurun_out/r02_sanitizer.txt
