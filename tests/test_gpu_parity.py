@@ -419,3 +419,20 @@ def test_mask_share_generate_host(ctx, oracle, name, mk, mask_kind):
             assert np.array_equal(emask, np.asarray(omask, dtype=np.int64))
         assert np.array_equal(mask, emask), (name, mask_kind, dim)
         assert np.array_equal(shares, ctx.share_generate(ss, emasked, sseed)), (name, mask_kind, dim)
+
+
+def test_mask_share_generate_errors(ctx):
+    """the fused entry point keeps the reference's failure modes: chacha.rs:26 (scheme dimension != number of secrets),
+    an invalid sharing scheme, an invalid masking modulus"""
+    ss = params.config3()
+    secrets = np.arange(10, dtype=np.int64)
+    with pytest.raises(SdaClientError, match="chacha.rs:26"):
+        ctx.mask_share_generate(LMS.ChaCha(P61, 11, 128), ss, secrets, b"\1" * 32, b"\2" * 32)
+    with pytest.raises(SdaClientError, match="low >= high"):
+        ctx.mask_share_generate(LMS.Full(0), ss, secrets, b"\1" * 32, b"\2" * 32)
+    bad = LSS.PackedShamir(3, 5, 2, P61, 1, ss.c.omega_shares)                       # secret points collide
+    with pytest.raises(SdaClientError, match="omega_secrets has order"):
+        ctx.mask_share_generate(LMS.Full(P61), bad, secrets, b"\1" * 32, b"\2" * 32)
+    # an empty vector is not an error: no mask, no shares
+    mask, shares = ctx.mask_share_generate(LMS.Full(P61), ss, np.zeros(0, dtype=np.int64), b"\1" * 32, b"\2" * 32)
+    assert len(mask) == 0 and shares.shape == (5, 0)
