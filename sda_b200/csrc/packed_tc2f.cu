@@ -1,14 +1,14 @@
 // packed_tc2f.cu -- share generation fused with the clerk sums (participate.rs:75-76 + clerk.rs:71-86 on one box) on the
 // paired-tile machinery of packed_tc2.cuh: the second generation of packed_tc.cu's packed_share_combine_tc_kernel.
 //
-// A CTA owns one pass of batches (Shape2::PASS of them: one or two E/O tile pairs) and walks the participants: for each it
+// A CTA owns one pass of batches (256 of them: one E/O tile pair) and walks the participants: for each it
 // stages that participant's secrets and draws of the pass as operand tiles exactly as the share-generation kernel does and
 // multiplies them into the SAME TMEM accumulators (tcgen05.mma with accumulate).  No share is ever folded or stored per
 // participant: the limb sums keep growing (at most 8 (k + t) 255^2 per participant and limb, so 256 participants fit the
 // s32 accumulators), are drained every 256 participants and at the end -- composed with 64-bit arithmetic and added to the
-// running sums of the pass, which live in the output between drains.  Per participant a
-// thread's work is its share of the keystream (one block for t = 4), the staging of 2k secrets and one barrier: the kernel is
-// the keystream plus ~10 %.
+// running sums of the pass, which live in the output between drains.  Per participant a thread's work is its share of the
+// keystream (one block for t = 4), the staging of 2k secrets and one barrier: the kernel is the keystream plus ~12 %
+// (profiles/r02_fused.md).
 //
 // A pass is ONE tile pair (256 batches: two 64-column accumulators, four CTAs per SM by TMEM for n <= 8); where that leaves a
 // participant's pass fewer keystream blocks than the CTA has threads (t = 2: 64), GP = 2 participants are staged and
@@ -54,6 +54,7 @@ struct FusedShape2 {
     static constexpr int GP = S::NBLK < CTA2 ? CTA2 / S::NBLK : 1;       // participants per step
     static_assert(GP * S::NBLK >= CTA2 || S::NBLK % CTA2 == 0 || GP == 1, "keystream blocks per step");
     static constexpr int TCOLS = 2 * S::ACC_COLS;                        // accumulators E and O
+    static_assert((long long)MAX_ACCUM2 * 8 * (K + T) * 255 * 255 < (1ll << 31), "limb sums of a full accumulation fit s32");
     static constexpr uint32_t D_BYTES = GP * S::D_BYTES, S_BYTES = GP * S::S_BYTES, IN_BYTES = GP * S::IN_BYTES;
     static constexpr uint32_t SMEM = 2 * D_BYTES + S_BYTES + 2 * S::B_IMG + IN_BYTES;
     static constexpr int BY_SMEM = SMEM + 1152 > 227 * 1024 / 2 ? 1 : SMEM + 1152 > 227 * 1024 / 3 ? 2 : SMEM + 1152 > 227 * 1024 / 4 ? 3 : 4;
