@@ -13,12 +13,17 @@
 //     are (for odd K the middle word serves both rows; the constant operand has a zero where the neighbour's
 //     secret sits, hence two operand images, E and O);
 //   * the limbs of the constant operand are not 8 x 8 bits: widths (8,8,8,8,8,W5,8,13-W5) with W5 chosen per
-//     k + t so that  e0 + e1 2^16 + e2 2^32  fits one IMAD.WIDE whose addend is the register PAIR (e0, e2) and the
-//     top term folds with one mask and one shift -- 14 instructions per share and one wide multiply instead of
+//     k + t so that  e0 + e1 2^16 + e2 2^32  stays below 2^61: a shift-and-add pair on the register PAIR (e0, e2), and
+//     the top term folds with one mask and one shift -- 15 instructions per share and no wide multiply instead of
 //     16 and two (tests/test_k2_model.py restates it with Python integers and checks every bound);
-//   * store addresses are a uniform 64-bit base plus a 32-bit per-thread offset;
+//   * store addresses are a running 64-bit pointer per thread (one add per share row);
 //   * pass bookkeeping ((participant, pass) of the next unit, "does this pass lie inside the vector") is 32-bit and
-//     warp-uniform, and the MMAs are issued from warp-uniform code (elect.sync) with uniform descriptors.
+//     warp-uniform, and the MMAs are issued from warp-uniform code (elect.sync) with uniform descriptors;
+//   * the keystream block is fully unrolled and starts from per-participant first-round constants (chacha_pre.cuh).
+//
+// The same kernel serves, by template flags: RTN -- the share count at run time for every (k, t) with k + t <= 16
+// (packed_tc2n.cu); MASKED -- the participant's mask drawn and added while the secrets are staged (packed_tc2m.cu).  The
+// share-gen -> clerk-sum kernel of packed_tc2f.cu is built from the same pieces.
 //
 // Shared memory per CTA (k=3, t=2, n=5): draws 2 x 8 KB, secrets 16 KB, two operand images 6 KB, raw secrets of
 // the coming pass 12 KB = 51 KB, four CTAs per SM (TMEM: two 64-column accumulators each).
