@@ -38,4 +38,9 @@ timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pyte
   > gpurun_out/sanitize_memcheck_fused2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_fused2.log
 timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
   -k "share_generate_combine or (tmem_accumulation and cfg3)" > gpurun_out/sanitize_racecheck_fused2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_fused2.log
+# the paired reveal kernel (16-byte share loads, two accumulators, bulk stores)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py tests/test_gpu_parity.py -q -m gpu \
+  -k "reveal_many_tiles or (reconstruct_generic and (shape0 or shape3 or shape5 or shape9))" > gpurun_out/sanitize_memcheck_reveal2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_memcheck_reveal2.log
+timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_device.py -q -m gpu \
+  -k "reveal_many_tiles and cfg5" > gpurun_out/sanitize_racecheck_reveal2.log 2>&1; echo "rc=$?" >> gpurun_out/sanitize_racecheck_reveal2.log
 (echo "compute-sanitizer on a B200 (tools/gpu_sanitize.sh), round 2"; for f in gpurun_out/sanitize_*.log; do echo "== $(basename $f)"; grep -v "^$" $f | tail -6; done) > gpurun_out/r02_sanitizer.txt
