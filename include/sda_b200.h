@@ -62,7 +62,8 @@ enum {
     SDA_ERR_INVALID = 1,     /* the reference returns Err(..) or panics on this input */
     SDA_ERR_CUDA = 2,        /* CUDA runtime / driver failure (incl. no device) */
     SDA_ERR_NCCL = 3,        /* NCCL failure (incl. libnccl.so.2 not loadable) in a multi-GPU entry point */
-    SDA_ERR_UNSUPPORTED = 4  /* parameters outside what the kernels implement */
+    SDA_ERR_UNSUPPORTED = 4, /* parameters outside what the kernels implement */
+    SDA_ERR_REJECTED = 5     /* deferred checks only: gen_range rejected a word in an earlier *_dev call (see below) */
 };
 
 enum { SDA_SHARING_ADDITIVE = 0, SDA_SHARING_PACKED_SHAMIR = 1 };
@@ -113,6 +114,15 @@ int         sda_ctx_set_packed_path(sda_ctx *ctx, int path);
 int         sda_ctx_set_stream(sda_ctx *ctx, void *cuda_stream);
 void       *sda_ctx_get_stream(const sda_ctx *ctx);
 int         sda_ctx_synchronize(sda_ctx *ctx);
+/* Deferred rejection checks.  A *_dev entry point that draws randomness normally ends with one stream synchronisation:
+ * it reads the flag that says whether rand-0.3's gen_range would have rejected a keystream word (probability ~2^-57 per
+ * draw), and redoes the call on the exact path if so.  With deferred checks ON those entry points only QUEUE their work
+ * and the copy of their flag word and return at once (calls overlap, small vectors do not pay a round trip each);
+ * sda_ctx_synchronize() then waits for the stream and looks at every queued flag: SDA_OK, or SDA_ERR_REJECTED naming
+ * the first affected call, whose outputs the caller must recompute with deferred checks off.  Host-buffer entry points,
+ * the varint codec and an in-place sda_share_generate_combine_dev are never deferred.  Switching the mode checks what is
+ * pending and returns that status. */
+int         sda_ctx_set_deferred_checks(sda_ctx *ctx, int on);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t    sda_ctx_launch_count(const sda_ctx *ctx);
 /* kernel variant the last sharing call dispatched to ("packed<3,2,5>/mersenne61", ...) */
@@ -189,7 +199,8 @@ int sda_unmask(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *mask, s
 /* ---- device-pointer entry points (what the benchmark times) ---------------------------- */
 /* All pointers are device memory of the context's device; launches go to the context's
  * stream.  Calls that draw randomness synchronise that stream once at the end to read the
- * gen_range rejection flag (and redo the call on the exact path if it is set). */
+ * gen_range rejection flag (and redo the call on the exact path if it is set) -- unless the context
+ * runs with deferred checks (sda_ctx_set_deferred_checks). */
 
 /* ShareGenerator::generate for P participants at once: secrets[P][dim] (row stride
  * secrets_ld elements), seeds[P][32] (HOST memory), shares_out[P][output_size][B]. */

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SDA_B200_LIB: developer override to A/B another build of the same library
 LIB_PATH = os.environ.get("SDA_B200_LIB") or os.path.join(_HERE, "libsda_b200.so")
 
-SDA_OK, SDA_ERR_INVALID, SDA_ERR_CUDA, SDA_ERR_NCCL, SDA_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+SDA_OK, SDA_ERR_INVALID, SDA_ERR_CUDA, SDA_ERR_NCCL, SDA_ERR_UNSUPPORTED, SDA_ERR_REJECTED = 0, 1, 2, 3, 4, 5
 SHARING_ADDITIVE, SHARING_PACKED_SHAMIR = 0, 1
 MASK_NONE, MASK_FULL, MASK_CHACHA = 0, 1, 2
 PACKED_PATH_AUTO, PACKED_PATH_CUDA_CORES, PACKED_PATH_TENSOR_CORES, PACKED_PATH_TENSOR_CORES_V1 = 0, 1, 2, 3
@@ -44,6 +44,7 @@ PROTOTYPES = {
     "sda_ctx_set_stream": (_int, [_vp, _vp]),
     "sda_ctx_get_stream": (_vp, [_vp]),
     "sda_ctx_synchronize": (_int, [_vp]),
+    "sda_ctx_set_deferred_checks": (_int, [_vp, _int]),
     "sda_ctx_launch_count": (_u64, [_vp]),
     "sda_ctx_last_kernel": (C.c_char_p, [_vp]),
     "sda_host_alloc": (_int, [_vp, _sz, C.POINTER(_vp)]),

@@ -189,6 +189,11 @@ class Context:
     def synchronize(self):
         self.check(self._lib.sda_ctx_synchronize(self._h))
 
+    def set_deferred_checks(self, on):
+        """*_dev calls that draw randomness stop synchronising; `synchronize()` reports a rejected keystream word (raises
+        SdaClientError with code SDA_ERR_REJECTED) for the calls queued since"""
+        self.check(self._lib.sda_ctx_set_deferred_checks(self._h, 1 if on else 0))
+
     def launch_count(self):
         return self._lib.sda_ctx_launch_count(self._h)
 

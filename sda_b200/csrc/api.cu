@@ -96,6 +96,13 @@ struct sda_ctx {
     Matrix m_cached;
     unsigned *d_flag = nullptr;    // [0] rejection flag, [1] draw_exact status
     unsigned *h_flag = nullptr;    // pinned mirror
+    // deferred rejection checks (sda_ctx_set_deferred_checks): the *_dev entry points queue their flag word into h_ring and
+    // return without synchronising; sda_ctx_synchronize looks at what is pending
+    bool deferred = false;
+    int dev_entry_depth = 0;       // > 0 inside a *_dev entry point (host entry points never defer: they hand results out)
+    unsigned *h_ring = nullptr;    // pinned, DEFER_RING words
+    uint64_t seq_issued = 0, seq_checked = 0;
+    bool forced_pending = false;   // SDA_B200_DEBUG_FORCE_REJECT=1 seen by a deferred call
     PinBuf stage[2];               // pinned staging for pageable host buffers
     // multi-GPU: the NCCL communicator this context is a rank of, and -- for the one-process form
     // (sda_ctx_create_multi) -- the member contexts of the other devices, owned by member 0
@@ -343,6 +350,43 @@ int read_flags(sda_ctx *ctx, unsigned *rejected, unsigned *status) {
     CU(cudaStreamSynchronize(ctx->stream));
     if (rejected) *rejected = ctx->h_flag[0];
     if (status) *status = ctx->h_flag[1];
+    return SDA_OK;
+}
+
+constexpr uint64_t DEFER_RING = 4096;
+struct DevEntry {                      // scope of a *_dev entry point
+    sda_ctx *c;
+    explicit DevEntry(sda_ctx *ctx) : c(ctx) { c->dev_entry_depth++; }
+    ~DevEntry() { c->dev_entry_depth--; }
+};
+// look at every deferred flag word: synchronises the stream
+int resolve_deferred(sda_ctx *ctx) {
+    if (ctx->seq_issued == ctx->seq_checked && !ctx->forced_pending) return SDA_OK;
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint64_t bad = ~0ull;
+    for (uint64_t q = ctx->seq_checked; q < ctx->seq_issued; q++)
+        if (ctx->h_ring[q % DEFER_RING] != 0 && bad == ~0ull) bad = q;
+    if (ctx->forced_pending && bad == ~0ull) bad = ctx->seq_checked;
+    ctx->seq_checked = ctx->seq_issued;
+    ctx->forced_pending = false;
+    if (bad != ~0ull)
+        return fail(ctx, SDA_ERR_REJECTED, "gen_range rejected a keystream word in deferred call #%llu (counted from the switch to "
+                    "deferred checks): the outputs of that call are not the reference's; redo it with deferred checks off",
+                    (unsigned long long)bad);
+    return SDA_OK;
+}
+// the rejection flag of the call just queued: read now (synchronises), or -- inside a *_dev entry point of a context with
+// deferred checks -- copied into the ring for sda_ctx_synchronize to look at, reporting "not rejected" for now
+int finish_flagged(sda_ctx *ctx, unsigned *rejected, bool may_defer = true) {
+    if (!(ctx->deferred && ctx->dev_entry_depth > 0 && may_defer)) {
+        OK(read_flags(ctx, rejected, nullptr));
+        return SDA_OK;
+    }
+    if (ctx->seq_issued - ctx->seq_checked >= DEFER_RING) OK(resolve_deferred(ctx));
+    CU(cudaMemcpyAsync(ctx->h_ring + ctx->seq_issued % DEFER_RING, ctx->d_flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->seq_issued++;
+    if (ctx->debug_force_reject) ctx->forced_pending = true;
+    *rejected = 0;
     return SDA_OK;
 }
 
@@ -608,7 +652,7 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
         OK(clear_flags(ctx));
         OK(launch_share_tc(ctx, pk, M, f, dr, d_secrets, ld, P, dim, 0, B, d_keys, d_out));
         unsigned rejected = 0;
-        OK(read_flags(ctx, &rejected, nullptr));
+        OK(finish_flagged(ctx, &rejected));
         exact = rejected != 0;
     } else if (fast) {
         OK(clear_flags(ctx));
@@ -623,7 +667,7 @@ int share_generate_core(sda_ctx *ctx, const sda_sharing_scheme *s, const int64_t
                                        dim, d_keys + p0, nullptr, nullptr, d_out + p0 * (size_t)n * B, ctx->d_flag));
         }
         unsigned rejected = 0;
-        OK(read_flags(ctx, &rejected, nullptr));
+        OK(finish_flagged(ctx, &rejected));
         exact = rejected != 0;
     }
     if (!exact) return SDA_OK;
@@ -764,7 +808,7 @@ int mask_core(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_secret
     OK(clear_flags(ctx));
     CU(launch_mask(ctx->lc(), f, dr, rounds, d_secrets, dim, key, nullptr, mask_dst, d_masked_out, ctx->d_flag, d_x, frac_bits));
     unsigned rejected = 0;
-    OK(read_flags(ctx, &rejected, nullptr));
+    OK(finish_flagged(ctx, &rejected));
     if (!rejected) return SDA_OK;
     if (d_x) {   // the exact path reads i64 secrets: encode first, then mask in place
         CU(launch_fixed_encode(ctx->lc(), f, frac_bits, d_x, dim, d_masked_out));
@@ -799,7 +843,7 @@ int chacha_mask_combine_core(sda_ctx *ctx, const sda_masking_scheme *s, const in
     CU(launch_chacha_mask_combine(ctx->lc(), f, dr, (const ChaChaKey *)ctx->keys.p, P, dim, d_out,
                                   (int64_t *)ctx->scratch.p, se, ctx->d_flag));
     unsigned rejected = 0;
-    OK(read_flags(ctx, &rejected, nullptr));
+    OK(finish_flagged(ctx, &rejected));
     if (!rejected) return SDA_OK;
     // exact: out = sum over seeds of the exact stream
     CU(ctx->draws.reserve(dim * sizeof(uint64_t)));
@@ -985,6 +1029,7 @@ void sda_ctx_destroy(sda_ctx *ctx) {
     ctx->stage[1].release();
     if (ctx->d_flag) cudaFree(ctx->d_flag);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
     for (int i = 0; i < 4; i++)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
@@ -1021,7 +1066,15 @@ int sda_ctx_synchronize(sda_ctx *ctx) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
     CU(cudaStreamSynchronize(ctx->stream));
-    return SDA_OK;
+    return resolve_deferred(ctx);
+}
+int sda_ctx_set_deferred_checks(sda_ctx *ctx, int on) {
+    if (!ctx) return SDA_ERR_INVALID;
+    DeviceGuard g(ctx->device);
+    if (on && !ctx->h_ring) CU(cudaMallocHost((void **)&ctx->h_ring, DEFER_RING * sizeof(unsigned)));
+    const int rc = resolve_deferred(ctx);      // nothing stays pending across a switch
+    ctx->deferred = on != 0;
+    return rc;
 }
 uint64_t sda_ctx_launch_count(const sda_ctx *ctx) { return ctx ? ctx->nlaunch : 0; }
 const char *sda_ctx_last_kernel(const sda_ctx *ctx) { return ctx ? ctx->kernel_name : ""; }
@@ -1097,6 +1150,7 @@ int sda_share_generate_dev(sda_ctx *ctx, const sda_sharing_scheme *s, const int6
                            size_t P, size_t dim, const uint8_t *seeds, int64_t *d_shares_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
     return share_generate_core(ctx, s, d_secrets, secrets_ld, P, dim, seeds, d_shares_out);
 }
@@ -1111,6 +1165,7 @@ int sda_mask_share_generate_dev(sda_ctx *ctx, const sda_masking_scheme *ms, cons
                                 int64_t *d_shares_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
     OK(mask_validate(ctx, ms));
     Packed pk;
@@ -1162,8 +1217,8 @@ int sda_mask_share_generate_dev(sda_ctx *ctx, const sda_masking_scheme *ms, cons
                                           (uint32_t *)ctx->keys_pre.p, (const uint8_t *)ctx->tc2_image.p,
                                           ms->kind == SDA_MASK_FULL ? d_masks_out : nullptr, d_shares_out, ctx->d_flag));
         unsigned rejected = 0;
-        OK(read_flags(ctx, &rejected, nullptr));
-        if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)
+        OK(finish_flagged(ctx, &rejected));
+        if (ctx->debug_force_reject && !(ctx->deferred && ctx->dev_entry_depth > 0)) rejected = 1;   // test hook: exercise the redo
         if (!rejected) return SDA_OK;
     }
     // one participant at a time through a scratch vector
@@ -1196,6 +1251,7 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
                                    const int64_t *d_acc_in, int64_t *d_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     OK(validate(ctx, s, nullptr));
     if (secrets_ld < dim) return fail(ctx, SDA_ERR_INVALID, "secrets_ld < dim");
     const size_t n = s->share_count, B = sda_share_batches(s, dim);
@@ -1241,8 +1297,9 @@ int sda_share_generate_combine_dev(sda_ctx *ctx, const sda_sharing_scheme *s, co
                                                   d_dst, ctx->d_flag, (uint32_t *)ctx->keys_pre.p));
             }
             unsigned rejected = 0;
-            OK(read_flags(ctx, &rejected, nullptr));
-            if (ctx->debug_force_reject) rejected = 1;   // test hook: exercise the redo (SDA_B200_DEBUG_FORCE_REJECT=1)
+            // (in place the copy below waits for the flag: such a call is never deferred)
+            OK(finish_flagged(ctx, &rejected, d_dst == d_out));
+            if (ctx->debug_force_reject && !(ctx->deferred && ctx->dev_entry_depth > 0 && d_dst == d_out)) rejected = 1;   // test hook
             if (!rejected) {
                 if (d_dst != d_out)
                     CU(cudaMemcpyAsync(d_out, d_dst, n * B * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1295,6 +1352,7 @@ int sda_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_t *d_sec
                  const uint8_t rng_seed[32], int64_t *d_mask_out, int64_t *d_masked_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     if (s && s->kind == SDA_MASK_CHACHA) {
         int64_t words[8] = {0};
         OK(mask_core(ctx, s, d_secrets, dim, rng_seed, nullptr, words, d_masked_out));
@@ -1313,6 +1371,7 @@ int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t
                               int64_t *d_masked_out, size_t masked_ld) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     OK(mask_validate(ctx, s));
     if (modulus <= 0) return fail(ctx, SDA_ERR_INVALID, "modulus must be positive");
     if (frac_bits < 0 || frac_bits > 52) return fail(ctx, SDA_ERR_INVALID, "frac_bits must be in [0, 52]");
@@ -1357,7 +1416,8 @@ int sda_fixed_encode_mask_dev(sda_ctx *ctx, const sda_masking_scheme *s, int64_t
     if (!words.empty() && d_mask_out)
         CU(cudaMemcpyAsync(d_mask_out, words.data(), words.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     unsigned rejected = 0;
-    OK(read_flags(ctx, &rejected, nullptr));        // also: `words` has been copied
+    if (!words.empty()) CU(cudaStreamSynchronize(ctx->stream));     // `words` has been copied
+    OK(finish_flagged(ctx, &rejected));
     if (!rejected) return SDA_OK;
     // a rejected gen_range word somewhere: redo participant by participant on the exact path
     for (size_t p = 0; p < P; p++) {
@@ -1372,6 +1432,7 @@ int sda_mask_combine_dev(sda_ctx *ctx, const sda_masking_scheme *s, const int64_
                          int64_t *d_out) {
     if (!ctx) return SDA_ERR_INVALID;
     DeviceGuard g(ctx->device);
+    DevEntry dev_entry(ctx);
     OK(mask_validate(ctx, s));
     switch (s->kind) {
     case SDA_MASK_NONE:
@@ -1587,8 +1648,12 @@ int sda_mask_share_generate(sda_ctx *ctx, const sda_masking_scheme *ms, const sd
     CU(ctx->out.reserve(std::max<size_t>(out_len, 1) * sizeof(int64_t)));
     CU(ctx->aux.reserve(std::max<size_t>(mask_len, 1) * sizeof(int64_t)));
     if (dim) OK(h2d(ctx, ctx->in.p, secrets, dim * sizeof(int64_t)));
-    OK(sda_mask_share_generate_dev(ctx, ms, ss, (const int64_t *)ctx->in.p, ldp, 1, dim, mask_rng_seed, share_rng_seed,
-                                   (int64_t *)ctx->aux.p, (int64_t *)ctx->out.p));
+    const bool was_deferred = ctx->deferred;      // a host entry point hands its results out: its flag is read now
+    ctx->deferred = false;
+    const int rc = sda_mask_share_generate_dev(ctx, ms, ss, (const int64_t *)ctx->in.p, ldp, 1, dim, mask_rng_seed, share_rng_seed,
+                                               (int64_t *)ctx->aux.p, (int64_t *)ctx->out.p);
+    ctx->deferred = was_deferred;
+    OK(rc);
     if (mask_len) OK(d2h(ctx, mask_out, ctx->aux.p, mask_len * sizeof(int64_t)));
     if (out_len) OK(d2h(ctx, shares_out, ctx->out.p, out_len * sizeof(int64_t)));
     return SDA_OK;

@@ -590,3 +590,59 @@ def test_masked_pipeline_reveals_the_sum(ctx, oracle, torch_cuda, mk, mask_kind)
     ctx.share_combine_dev(LSS.Additive(2, p), d_sec, dim, P, dim, d_tot)
     ctx.synchronize()
     assert t.equal(d_out, d_tot)
+
+
+def test_deferred_rejection_checks(oracle, torch_cuda, monkeypatch):
+    """sda_ctx_set_deferred_checks: *_dev calls that draw randomness return without a stream synchronisation and produce the same
+    results; synchronize() reports SDA_OK -- or, with the rejection flag forced, SDA_ERR_REJECTED for the queued calls; the
+    host entry points of the same context still check at once"""
+    import sda_b200
+    from sda_b200 import _lib
+    t = torch_cuda
+    ss, dim, P = params.config3(), 30_000, 4
+    ms = LMS.Full(ss.modulus)
+    rng = np.random.default_rng(9)
+    secrets = rng.integers(0, ss.modulus, size=(P, dim), dtype=np.int64)
+    seeds = b"".join(util.seed_bytes(f"df/{pi}") for pi in range(P))
+    n, B = ss.output_size(), ss.batches(dim)
+
+    def run(c):
+        d_sh = t.empty((P, n, B), dtype=t.int64, device="cuda")
+        d_mask, d_masked = t.empty(dim, dtype=t.int64, device="cuda"), t.empty(dim, dtype=t.int64, device="cuda")
+        d_acc = t.empty((n, B), dtype=t.int64, device="cuda")
+        d_sh3 = t.empty((P, 3, dim), dtype=t.int64, device="cuda")
+        for _ in range(3):                                     # several calls queued back to back
+            c.share_generate_dev(ss, dev(t, secrets), dim, P, dim, seeds, d_sh)
+            c.mask_dev(ms, dev(t, secrets[0]), dim, seeds[:32], d_mask, d_masked)
+            c.share_generate_combine_dev(ss, dev(t, secrets), dim, P, dim, seeds, d_acc)
+            c.share_generate_dev(LSS.Additive(3, ss.modulus), dev(t, secrets), dim, P, dim, seeds, d_sh3)
+        return d_sh, d_mask, d_masked, d_acc, d_sh3
+
+    plain = sda_b200.Context(0)
+    ref = run(plain)
+    plain.synchronize()
+    deferred = sda_b200.Context(0)
+    deferred.set_deferred_checks(True)
+    got = run(deferred)
+    deferred.synchronize()                                     # SDA_OK: nothing was rejected
+    for a, b in zip(ref, got):
+        assert t.equal(a, b)
+    exp = util.oracle_generate(oracle, ss, secrets[2], seeds[64:96], matrix=True)
+    assert np.array_equal(host(got[0][2]), util.canon(oracle, ss.modulus, exp))
+    # a host entry point of a deferred context checks at once and is exact
+    assert np.array_equal(deferred.share_generate(ss, secrets[1], seeds[32:64]), host(ref[0][1]))
+    deferred.set_deferred_checks(False)
+    # forced flag: the deferred calls report it at the next synchronisation, not before
+    monkeypatch.setenv("SDA_B200_DEBUG_FORCE_REJECT", "1")
+    forced = sda_b200.Context(0)
+    monkeypatch.delenv("SDA_B200_DEBUG_FORCE_REJECT")
+    forced.set_deferred_checks(True)
+    d_sh = t.empty((P, n, B), dtype=t.int64, device="cuda")
+    d_masks = t.empty((P, dim), dtype=t.int64, device="cuda")
+    forced.mask_share_generate_dev(ms, ss, dev(t, secrets), dim, P, dim, seeds, seeds, d_masks, d_sh)    # returns SDA_OK
+    with pytest.raises(sda_b200.SdaClientError, match="deferred call #0") as ei:
+        forced.synchronize()
+    assert ei.value.code == _lib.SDA_ERR_REJECTED
+    forced.synchronize()                                       # reported once; nothing pending any more
+    for c in (plain, deferred, forced):
+        c.close()
