@@ -22,6 +22,7 @@ pub const SDA_ERR_INVALID: c_int = 1;
 pub const SDA_ERR_CUDA: c_int = 2;
 pub const SDA_ERR_NCCL: c_int = 3;
 pub const SDA_ERR_UNSUPPORTED: c_int = 4;
+pub const SDA_ERR_REJECTED: c_int = 5;      // deferred checks: a *_dev call queued earlier must be redone
 
 pub const SDA_SHARING_ADDITIVE: i32 = 0;
 pub const SDA_SHARING_PACKED_SHAMIR: i32 = 1;
@@ -97,6 +98,8 @@ pub mod ffi {
         pub fn sda_ctx_destroy(ctx: *mut SdaCtx);
         pub fn sda_last_error(ctx: *const SdaCtx) -> *const c_char;
         pub fn sda_ctx_set_rng_rounds(ctx: *mut SdaCtx, rounds: c_int) -> c_int;
+        pub fn sda_ctx_synchronize(ctx: *mut SdaCtx) -> c_int;
+        pub fn sda_ctx_set_deferred_checks(ctx: *mut SdaCtx, on: c_int) -> c_int;
         pub fn sda_host_alloc(ctx: *mut SdaCtx, bytes: usize, out: *mut *mut c_void) -> c_int;
         pub fn sda_host_free(ctx: *mut SdaCtx, ptr: *mut c_void) -> c_int;
 
