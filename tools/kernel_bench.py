@@ -196,6 +196,22 @@ def main():
             ctx.set_rng_rounds(args.rounds)
             del sec, sh
             torch.cuda.empty_cache()
+        # ---- small calls: what the per-call flag read-back costs, and what deferred checks give back ------------------------
+        s3, P, dim = params.config3(), 4, 100_000
+        sec = empty(P, dim)
+        ctx.synth_fill_dev(12, P61, 0, P * dim, sec)
+        sh = empty(P, s3.output_size(), s3.batches(dim))
+        masks, masked = empty(dim), empty(dim)
+        sd = seeds("small", P)
+        fm = LMS.Full(P61)
+        for deferred in (False, True):
+            ctx.set_deferred_checks(deferred)
+            tag = "deferred checks" if deferred else "flag read back per call"
+            timeit(f"small call: packed_share cfg3 [4][100k] ({tag})", lambda: ctx.share_generate_dev(s3, sec, dim, P, dim, sd, sh),
+                   P * dim, P * (dim + s3.output_size() * s3.batches(dim)) * 8)
+            timeit(f"small call: full_mask [100k] ({tag})", lambda: ctx.mask_dev(fm, sec[0], dim, sd[:32], masks, masked), dim, dim * 24)
+        ctx.set_deferred_checks(False)
+        del sec, sh, masks, masked
         # ---- additive split with a share count beyond the unrolled kernels (n = 9) ---------------------------------------
         s9, P, dim = LSS.Additive(9, P61), 128, 1_000_000
         sec = empty(P, dim)
