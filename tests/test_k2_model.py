@@ -363,3 +363,106 @@ def test_packed_tc2_pair_layout_maps_every_draw_and_secret_once():
             for slot_i, el in enumerate(o_elems):
                 idx = slot_i - (k & 1)                                    # image O: half a chunk late for odd k
                 assert el == base + k + idx
+
+
+# ---- packed_tc2f.cu: limb sums accumulated over participants, composed once per drain ------------------------------
+def compose_wide2(d, w5):
+    """compose_wide2<W5> of packed_tc2f.cu, word for word"""
+    lo = d[0] + (d[1] << 8) + (d[2] << 16) + (d[3] << 24)
+    hi = d[4] + (d[5] << 8) + (d[6] << (8 + w5)) + (d[7] << (16 + w5))
+    assert lo < (1 << 56) and hi < (1 << 56)
+    v = lo + ((hi & LOW29) << 32) + (hi >> 29)
+    assert v <= M64
+    v = (v & P) + (v >> 61)
+    return v - P if v >= P else v
+
+
+def test_fused_accumulation_fits_s32_and_composes_exactly():
+    """MAX_ACCUM2 = 256 participants of limb sums fit the s32 accumulators for every k + t <= 16, and the wide compose of
+    the accumulated sums equals the sum of the participants' shares mod p"""
+    rng = random.Random(11)
+    for kt in range(2, 17):
+        w, pos = limb_plan2(kt)
+        for s in range(8):
+            assert 256 * 8 * kt * 255 * ((1 << w[s]) - 1) < (1 << 31)
+        crow = [rng.randrange(P) for _ in range(kt)]
+        acc, total = [0] * 8, 0
+        for _ in range(256):
+            xs = [rng.choice([M64, rng.randrange(1 << 64)]) for _ in range(kt)]
+            total += sum(c * x for c, x in zip(crow, xs))
+            for c, x in zip(crow, xs):
+                for byte in range(8):
+                    cst = c * pow(2, 8 * byte, P) % P
+                    xb = (x >> (8 * byte)) & 0xff
+                    for s in range(8):
+                        acc[s] += xb * ((cst >> pos[s]) & ((1 << w[s]) - 1))
+        assert max(acc) < (1 << 31)
+        assert compose_wide2(acc, w[5]) == total % P
+        assert compose_wide2([256 * 8 * kt * 255 * ((1 << w[s]) - 1) for s in range(8)], w[5]) < P     # every limb at its maximum
+
+
+# ---- packed_tc2m.cu / sharegen.cu: masks over 2^61 - 1 without a reduction -------------------------------------------
+def test_masked_operand_and_lazy_mask_sum_are_congruent():
+    """add_masks2: secret + ((v & p) + (v >> 61)) is a u64 congruent to the masked secret, for any i64 secret (negative ones
+    canonicalised first) and any accepted word v; chacha_mask_combine_kernel: the same terms summed 7 at a time before a fold
+    stay below 2^64 and reduce to the sum of gen_range's values.  Words in the flagged band are the host's business."""
+    rng = random.Random(12)
+    acc, exact, since = 0, 0, 0
+    for _ in range(20000):
+        v = rng.choice([rng.randrange(1 << 64), (rng.randrange(8) << 61) | ((1 << 61) - 9 - rng.randrange(1 << 16)), (1 << 64) - 9 - rng.randrange(100)])
+        hi, w1 = (v >> 32) & LOW29, v & 0xffffffff
+        if hi == LOW29 and w1 >= 0xfffffff8:
+            continue                                        # low 61 bits within 8 of 2^61: the kernels raise `flag`
+        assert v < (1 << 64) - 8                            # accepted by gen_range(0, p): zone = 2^64 - 8
+        sd = (v & P) + (v >> 61)
+        assert sd < P and sd == v % P                       # gen_range's value, no compare needed
+        secret = rng.choice([rng.randrange(P), -rng.randrange(1, 1 << 63), (1 << 63) - 1, P, 0])
+        x = secret if secret >= 0 else (secret % P)         # canon_negative
+        operand = x + sd
+        assert operand <= M64 and operand % P == (secret + v % P) % P
+        # the mask kernel's fast path: secret <= p, one conditional subtraction
+        if 0 <= secret <= P:
+            t = secret + sd
+            assert (t - P if t >= P else t) == (secret + sd) % P
+        acc += sd
+        exact += v % P
+        since += 1
+        assert acc <= M64
+        if since == 7:
+            acc, since = (acc & P) + (acc >> 61), 0
+    a = (acc & P) + (acc >> 61)
+    a = (a & P) + (a >> 61)
+    assert (a - P if a >= P else a) == exact % P
+
+
+def test_suspect_pairs_never_miss_a_flagged_word():
+    """suspect_of_block with SDA_TC2_SUSPECT_PAIRS: (w0_a | w0_b) & LOW29 == LOW29 is necessary for either word to have its
+    bits 0..28 all ones, so the running maximum over pairs reaches LOW29 whenever a single-word test would"""
+    rng = random.Random(13)
+    for _ in range(20000):
+        ws = [rng.choice([rng.randrange(1 << 32), LOW29 | (rng.randrange(8) << 29), 0xffffffff]) for _ in range(8)]
+        single = max(w & LOW29 for w in ws)
+        pairs = max((ws[d] | ws[d + 1]) & LOW29 for d in range(0, 8, 2))
+        assert pairs >= single and (single == LOW29) <= (pairs == LOW29)
+
+
+def test_float_encode_fast_path_matches_the_double_definition():
+    """mask_kernel<FLOAT_IN> over 2^61 - 1: rint(float(x) * float(2^f)) computed in float equals rint(double(x) * 2^f) (a
+    power-of-two scale is exact in float short of overflow, where both saturate), and q + (p & (q >> 63)) is the canonical
+    residue whenever |q| < 2^60"""
+    import numpy as np
+    rng = np.random.default_rng(14)
+    xs = np.concatenate([rng.standard_normal(20000).astype(np.float32) * np.float32(1000.0),
+                         np.array([0.0, -0.0, 1e-45, -1e-45, 2.0 ** 43, -2.0 ** 43, 2.0 ** 44 - 2.0 ** 21, 1.5 * 2.0 ** -16, 2.5 * 2.0 ** -16,
+                                   -0.5 * 2.0 ** -16, 65504.0, 1e20, -1e20], dtype=np.float32)])
+    for frac in (0, 16, 24, 40):
+        with np.errstate(over="ignore"):
+            qf = np.rint(xs * np.float32(2.0 ** frac))                       # float product, as the kernel forms it
+        qd = np.rint(xs.astype(np.float64) * 2.0 ** frac)
+        finite = np.isfinite(qf)
+        assert np.array_equal(qf[finite].astype(np.float64), qd[finite])     # the product is exact in float
+        assert (np.abs(qd[~finite]) >= 2.0 ** 63).all()                      # float overflow only where the double saturates too
+        small = np.abs(qd) < 2.0 ** 60
+        q = qd[small].astype(np.int64)
+        fast = (q.astype(object) + np.where(q < 0, P, 0).astype(object))
+        assert all(int(f) == int(v) % P for f, v in zip(fast[:2000], q[:2000]))
