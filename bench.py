@@ -591,6 +591,39 @@ def run_ours(args):
                 ts.append(a.elapsed_time(b))
             fused_ms = statistics.median(ts)
 
+        # the participant's two steps in one kernel (participate.rs:53-54 then :75-76): Full mask + share generation, the
+        # masked secrets never written.  Checked against sda_mask_dev followed by sda_share_generate_dev, then timed.
+        masked = None
+        if rank == 0 and world == 1 and not args.no_round_sweep and args.rounds == 20:
+            Tm = min(T, 64)
+            fm = sda_b200.LinearMaskingScheme.Full(p)
+            msd, ssd = seeds_for(-400, rank, Tm), seeds_for(-401, rank, Tm)
+            d_masks = torch.empty((Tm, dim), dtype=torch.int64, device="cuda")
+            ctx.mask_share_generate_dev(fm, scheme, d_sec, dim, Tm, dim, msd, ssd, d_masks, d_sh)
+            fused_kernel = ctx.last_kernel()
+            d_m0, d_md0 = torch.empty(dim, dtype=torch.int64, device="cuda"), torch.empty(dim, dtype=torch.int64, device="cuda")
+            d_s0 = torch.empty((n, B), dtype=torch.int64, device="cuda")
+            ctx.mask_dev(fm, d_sec[Tm - 1], dim, msd[32 * (Tm - 1):32 * Tm], d_m0, d_md0)
+            ctx.share_generate_dev(scheme, d_md0, dim, 1, dim, ssd[32 * (Tm - 1):32 * Tm], d_s0)
+            ctx.synchronize()
+            if not (torch.equal(d_masks[Tm - 1], d_m0) and torch.equal(d_sh[Tm - 1], d_s0)):
+                raise SystemExit("bench self-check failed: fused mask + share generation != mask then share generation")
+            ts = []
+            for i in range(3):
+                a, b = ev(), ev()
+                a.record(stream)
+                ctx.mask_share_generate_dev(fm, scheme, d_sec, dim, Tm, dim, seeds_for(-410 - i, rank, Tm), ssd, d_masks, d_sh)
+                b.record(stream)
+                ctx.synchronize()
+                ts.append(a.elapsed_time(b))
+            mms = statistics.median(ts)
+            masked = {"ms": mms, "participants": Tm, "elements_per_s": Tm * dim / (mms * 1e-3),
+                      "GBps": Tm * (2 * dim + n * B) * 8 / (mms * 1e-3) / 1e9, "kernel": fused_kernel,
+                      "note": "sda_mask_share_generate_dev: Full mask + share generation in one kernel, masked secrets never "
+                              "written to HBM (secrets in, masks and shares out); not part of `value`"}
+            del d_masks, d_m0, d_md0, d_s0
+            torch.cuda.empty_cache()
+
         # BASELINE config #2 beside it (additive 3-way split, dim 1M, 1024 participants, then one clerk's sum): the
         # additive kernels of the same path, device-resident, same timing method; reported under `kernels`, not in `value`
         cfg2 = None
@@ -782,6 +815,7 @@ def run_ours(args):
                                           "frac_of_hbm": T * dim * 8 / (fused_ms * 1e-3) / 1e9 / peak,
                                           "note": "sda_share_generate_combine_dev: reads 8 B per secret, shares never "
                                                   "materialised; not part of `value`"}} if fused_ms else {}),
+        **({"mask_share_gen_fused": dict(masked, frac_of_hbm=masked["GBps"] / peak)} if masked else {}),
         **({k: dict(v, frac_of_hbm=v["GBps"] / peak) for k, v in cfg2.items()} if cfg2 else {}),
         **({"config4_clerk_sum": cfg4} if cfg4 else {}), **({"config5_e2e": cfg5} if cfg5 else {}),
         "clerk_combine_x5": {"ms": comb_avg_ms, "share_elements_per_s": n * T * B / (comb_avg_ms * 1e-3),
