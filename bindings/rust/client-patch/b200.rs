@@ -171,6 +171,19 @@ impl SecretUnmasker for Masker {
     }
 }
 
+// ---- optional: the participant's two steps in one call --------------------------------------------------------------
+/// `participate.rs:53-54` (`secret_masker.mask(&secrets)`) followed by `:75-76` (`share_generator.generate(&masked)`):
+/// returns `(mask, shares per clerk)` with the same values as the two trait calls, but uploads the secrets once and --
+/// for the 2^61-1 shapes -- never writes the masked secrets anywhere.  `new_participation` can call this instead of
+/// the two lines when it wants the fast path; the traits above keep working unchanged.
+pub fn mask_and_share(masking: &LinearMaskingScheme, sharing: &LinearSecretSharingScheme, secrets: &[Secret])
+                      -> SdaClientResult<(Vec<Mask>, Vec<Vec<Share>>)> {
+    let ctx = context();
+    let (ms, ss) = (masking_scheme(masking), sharing_scheme(sharing));
+    ctx.validate(&ss).map_err(|e| e.message)?;
+    Ok(ctx.mask_share_generate(&ms, &ss, secrets, &seed(), &seed()).map_err(|e| e.message)?)
+}
+
 // ---- the six constructions: the new bodies of crypto/sharing/mod.rs:35-96 and crypto/masking/mod.rs:33-94 ---------
 //
 // impl ShareGeneratorConstruction<LinearSecretSharingScheme> for CryptoModule {
